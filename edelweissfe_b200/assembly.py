@@ -1,0 +1,166 @@
+"""Device-resident element set: the B200 counterpart of the reference's
+(elements dict + DofManager + VIJSystemMatrix + CSRGenerator) quartet for one element type.
+
+PyTorch owns the buffers; all arithmetic happens in libedelweiss_b200.so (hand-written CUDA,
+sm_100a) through the C ABI of include/edelweiss_b200.h.  No CPU fallback.
+
+Reference interfaces mirrored (paths below /root/reference/edelweissfe/):
+  numerics/dofmanager.py:445-471, 522-557     element dof lists, VIJ layout
+  numerics/csrgenerator.pyx:47-115            CSR pattern + updateCSR
+  solvers/nonlinearimplicitstatic.py:794-849  computeElements
+  elements/displacementelement/element.py:373-379   acceptLastState
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EwbBuffers, EwbError, check
+
+
+class CutbackRequest(Exception):
+    """Same meaning as edelweissfe.utils.exceptions.CutbackRequest(msg, cutbackSize)."""
+
+    def __init__(self, message, cutbackSize):
+        super().__init__(message)
+        self.cutbackSize = cutbackSize
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class ElementAssembly:
+    def __init__(self, elType, conn, coords, material, props, device="cuda:0", box=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise EwbError("edelweissfe_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device)
+        self.elType = elType.upper()
+        self.elCode = _lib.ELEMENT_CODES[self.elType]
+        self.material = material.lower()
+        self.matCode = _lib.MATERIAL_CODES[self.material]
+        self.props = np.ascontiguousarray(np.asarray(props, dtype=np.float64))
+        self.nn = _lib.ELEMENT_NODES[self.elCode]
+        self.nGp = _lib.ELEMENT_GAUSS[self.elCode]
+        self.nState = 12 + _lib.MATERIAL_NSTATE[self.matCode]
+        conn = np.ascontiguousarray(np.asarray(conn, dtype=np.int32))
+        assert conn.ndim == 2 and conn.shape[1] == self.nn
+        coords_t = torch.as_tensor(np.asarray(coords, dtype=np.float64)) if not torch.is_tensor(coords) else coords
+        self.nEl = conn.shape[0]
+        self.nNode = coords_t.shape[0]
+        self.nDof = 3 * self.nNode
+        self.nDofEl = 3 * self.nn
+        dev_index = self.device.index or 0
+        plan = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.ewb_plan_create(C.byref(plan), self.elCode, self.nEl, self.nNode, conn.ctypes.data_as(C.c_void_p), dev_index))
+        self.plan = plan
+        if box is not None:
+            check(self.lib.ewb_plan_set_box(self.plan, int(box[0]), int(box[1]), int(box[2])))
+        self.nnz = self.lib.ewb_plan_nnz(self.plan)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.coords = coords_t.to(**f64).contiguous()
+        self.U = torch.zeros(self.nDof, **f64)
+        self.dU = torch.zeros(self.nDof, **f64)
+        self.P = torch.zeros(self.nDof, **f64)
+        self.F = torch.zeros(self.nDof, **f64)
+        self.state_ref = torch.zeros(self.nState, self.nEl, self.nGp, **f64)
+        self.state_temp = torch.zeros(self.nState, self.nEl, self.nGp, **f64)
+        self.csr_data = torch.zeros(self.nnz, **f64)
+        self._pattern = None
+        self._props_c = self.props.ctypes.data_as(C.POINTER(C.c_double))
+
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None):
+                self.lib.ewb_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+    # ---- pattern ---------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def csr_pattern(self):
+        """(indptr, indices) int32 device tensors — CSRGenerator.__init__ (csrgenerator.pyx:47-98)."""
+        if self._pattern is None:
+            indptr = torch.empty(self.nDof + 1, dtype=torch.int32, device=self.device)
+            indices = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+            check(self.lib.ewb_plan_csr_pattern(self.plan, _ptr(indptr), _ptr(indices), self._stream()))
+            self._pattern = (indptr, indices)
+        return self._pattern
+
+    def slot_map(self, e0=0, e1=None):
+        """COO->CSR slot map x for elements [e0, e1) (csrgenerator.pyx:82-98)."""
+        e1 = self.nEl if e1 is None else e1
+        x = torch.empty((e1 - e0) * self.nDofEl**2, dtype=torch.int32, device=self.device)
+        check(self.lib.ewb_plan_slot_map(self.plan, e0, e1, _ptr(x), self._stream()))
+        return x
+
+    # ---- hot path ----------------------------------------------------------------------------
+    def _buffers(self, vij=None):
+        return EwbBuffers(_ptr(self.coords), _ptr(self.U), _ptr(self.dU), _ptr(self.state_ref), _ptr(self.state_temp),
+                          _ptr(self.csr_data), _ptr(self.P), _ptr(self.F), _ptr(vij))
+
+    def assemble(self, flags=0, vij=None, time=(0.0, 0.0), dT=0.0):
+        """One computeElements + updateCSR pass on the device (asynchronous on the current stream).
+        Results: self.csr_data, self.P, self.F, self.state_temp."""
+        buf = self._buffers(vij)
+        t = (C.c_double * 2)(*time)
+        check(self.lib.ewb_assemble(self.plan, self.matCode, self._props_c, len(self.props), C.byref(buf), t, float(dT), int(flags), self._stream()))
+
+    def poll(self):
+        """Synchronise and turn a device-side material failure into CutbackRequest (vonmises.py:230-231)."""
+        pnew = C.c_double(1.0)
+        rc = check(self.lib.ewb_poll_status(self.plan, self._stream(), C.byref(pnew)))
+        if rc == _lib.EWB_CUTBACK:
+            raise CutbackRequest(self.lib.ewb_last_error().decode(), pnew.value)
+
+    def compute_elements_vij(self, flags=0):
+        """Reference-layout outputs: V (VIJ values), Pe [nEl, nDofEl]."""
+        V = torch.empty(self.nEl * self.nDofEl**2, dtype=torch.float64, device=self.device)
+        Pe = torch.empty(self.nEl, self.nDofEl, dtype=torch.float64, device=self.device)
+        buf = self._buffers(V)
+        check(self.lib.ewb_compute_elements_vij(self.plan, self.matCode, self._props_c, len(self.props), C.byref(buf), _ptr(Pe), int(flags), self._stream()))
+        return V, Pe
+
+    def update_csr(self, V):
+        check(self.lib.ewb_update_csr(self.plan, _ptr(V), _ptr(self.csr_data), self._stream()))
+        return self.csr_data
+
+    def accept_last_state(self):
+        """acceptLastState for every element (element.py:373-379): stateTemp becomes stateRef."""
+        self.state_ref, self.state_temp = self.state_temp, self.state_ref
+
+    def apply_dirichlet_k(self, dofs):
+        d = torch.as_tensor(dofs, dtype=torch.int32, device=self.device).contiguous()
+        check(self.lib.ewb_apply_dirichlet_k(self.plan, _ptr(self.csr_data), _ptr(d), d.numel(), self._stream()))
+
+    # ---- state layout --------------------------------------------------------------------------
+    def state_aos(self, which="temp"):
+        """[nEl, nGp, nState] like the reference's per-element _stateVars* arrays."""
+        src = self.state_temp if which == "temp" else self.state_ref
+        out = torch.empty(self.nEl, self.nGp, self.nState, dtype=torch.float64, device=self.device)
+        check(self.lib.ewb_state_to_aos(_ptr(src), _ptr(out), self.nEl, self.nGp, self.nState, self._stream()))
+        return out
+
+    def set_state_aos(self, aos, which="ref"):
+        a = torch.as_tensor(aos, dtype=torch.float64).to(self.device).contiguous()
+        assert tuple(a.shape) == (self.nEl, self.nGp, self.nState)
+        dst = self.state_temp if which == "temp" else self.state_ref
+        check(self.lib.ewb_state_to_soa(_ptr(a), _ptr(dst), self.nEl, self.nGp, self.nState, self._stream()))
+
+    # ---- host round trips -----------------------------------------------------------------------
+    def to_scipy(self):
+        import scipy.sparse as sp
+
+        indptr, indices = self.csr_pattern()
+        return sp.csr_matrix((self.csr_data.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()), shape=(self.nDof, self.nDof))
+
+    def launch_count(self):
+        return int(self.lib.ewb_launch_count())

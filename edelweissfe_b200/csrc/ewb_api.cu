@@ -1,0 +1,445 @@
+// C ABI of libedelweiss_b200.so (see include/edelweiss_b200.h).  Host-side plan construction
+// (topology -> node adjacency -> CSR pattern, replacing DofManager._initializeVIJPattern and
+// CSRGenerator.__init__ of the reference) and kernel dispatch.  No torch types, no CPU fallback:
+// every compute entry point launches CUDA kernels or fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/edelweiss_b200.h"
+#include "ewb_generic.cuh"
+#include "ewb_sweep.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int64_t g_launches = 0;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) return fail(EWB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                    \
+    do {                                                                                  \
+        ++g_launches;                                                                     \
+        cudaError_t _e = cudaGetLastError();                                              \
+        if (_e != cudaSuccess) return fail(EWB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+    } while (0)
+
+template <class T>
+int upload(T** dst, const std::vector<T>& v) {
+    CUDA_TRY(cudaMalloc((void**)dst, std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return EWB_OK;
+}
+
+}  // namespace
+
+struct ewb_plan {
+    int device = 0;
+    int elType = 0;
+    int nn = 8, ngp = 8;
+    int64_t nEl = 0, nNode = 0, nnz = 0, nSlots = 0;
+    // device tables
+    int32_t* conn = nullptr;     // [nEl][nn]
+    int64_t* adjPtr = nullptr;   // [nNode+1]  node adjacency (sorted unique neighbour nodes, incl. self)
+    int32_t* adj = nullptr;      // [nSlots]
+    int64_t* incPtr = nullptr;   // [nNode+1]  node -> incident (element*nn + localNode), ascending element
+    int32_t* inc = nullptr;
+    int* failFlag = nullptr;     // device status word
+    int* failHost = nullptr;     // pinned mirror
+    double* peScratch = nullptr; // [nEl][3nn] per-element residual (generic path)
+    double* vijScratch = nullptr;
+    // structured (BoxGen) description
+    bool isBox = false;
+    int64_t nX = 0, nY = 0, nZ = 0;
+    std::vector<int32_t> connHost;
+    ewb::SweepPlan sweep;
+};
+
+namespace {
+
+int elementInfo(int elType, int* nn, int* ngp) {
+    switch (elType) {
+        case EWB_C3D8: *nn = 8; *ngp = 8; return EWB_OK;
+        case EWB_C3D8TL: *nn = 8; *ngp = 8; return EWB_OK;
+        case EWB_C3D20: *nn = 20; *ngp = 27; return EWB_OK;
+    }
+    return fail(EWB_ERR_UNSUPPORTED, "unknown element type");
+}
+
+int materialClass(int elType, int material, const double* props, int nProps, ewb::MatParams* mp, int* mc, int* nMatState) {
+    std::memset(mp, 0, sizeof(*mp));
+    mp->kind = material;
+    const bool tl = (elType == EWB_C3D8TL);
+    if (material == EWB_MAT_LINEARELASTIC || material == EWB_MAT_VONMISES) {
+        if (tl) return fail(EWB_ERR_UNSUPPORTED, "C3D8TL with hypo-elastic materials (geometric-stiffness branch, element.py:415-425) is not implemented");
+        if (nProps < (material == EWB_MAT_VONMISES ? 6 : 2)) return fail(EWB_ERR_ARG, "too few material properties");
+        const double E = props[0], v = props[1];
+        mp->lambda = E * v / ((1.0 + v) * (1.0 - 2.0 * v));
+        mp->G = E / (2.0 * (1.0 + v));
+        if (material == EWB_MAT_VONMISES) {
+            mp->fy0 = props[2]; mp->HLin = props[3]; mp->dfy = props[4]; mp->delta = props[5];
+            *mc = ewb::MC_VM; *nMatState = 1;
+        } else {
+            *mc = ewb::MC_LE; *nMatState = 0;
+        }
+        return EWB_OK;
+    }
+    if (material >= EWB_MAT_NEOHOOKE_WA && material <= EWB_MAT_NEOHOOKE_WC) {
+        if (!tl) return fail(EWB_ERR_UNSUPPORTED, "hyperelastic materials need the total-Lagrange element (element.py:333-334)");
+        if (nProps < 2) return fail(EWB_ERR_ARG, "too few material properties");
+        mp->mu = props[0]; mp->K = props[1];
+        *mc = ewb::MC_NH; *nMatState = 1;
+        return EWB_OK;
+    }
+    return fail(EWB_ERR_UNSUPPORTED, "unknown material");
+}
+
+template <int NN, int NGP, int MC, bool TL, int T, int E, int BLK>
+int launchVij(ewb_plan* p, const ewb::MatParams& mp, const ewb_buffers* b, double* V, double* Pe, cudaStream_t st) {
+    using L = ewb::TileLayout<NN, NGP, MC>;
+    auto kern = ewb::computeElementsVijKernel<NN, NGP, MC, TL, T, E, BLK>;
+    const size_t smem = (size_t)E * L::PER_EL * sizeof(double);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = (p->nEl + E - 1) / E;
+    kern<<<(unsigned)grid, T * E, smem, st>>>(p->nEl, p->conn, b->coords, b->U, b->dU, b->state_ref, b->state_temp, V, Pe, mp, p->failFlag);
+    LAUNCH_CHECK();
+    return EWB_OK;
+}
+
+int dispatchVij(ewb_plan* p, int mc, const ewb::MatParams& mp, const ewb_buffers* b, double* V, double* Pe, cudaStream_t st) {
+    if (p->elType == EWB_C3D8) {
+        if (mc == ewb::MC_LE) return launchVij<8, 8, ewb::MC_LE, false, 8, 16, 5>(p, mp, b, V, Pe, st);
+        if (mc == ewb::MC_VM) return launchVij<8, 8, ewb::MC_VM, false, 8, 16, 5>(p, mp, b, V, Pe, st);
+    } else if (p->elType == EWB_C3D8TL) {
+        if (mc == ewb::MC_NH) return launchVij<8, 8, ewb::MC_NH, true, 8, 16, 5>(p, mp, b, V, Pe, st);
+    } else if (p->elType == EWB_C3D20) {
+        if (mc == ewb::MC_LE) return launchVij<20, 27, ewb::MC_LE, false, 32, 4, 6>(p, mp, b, V, Pe, st);
+        if (mc == ewb::MC_VM) return launchVij<20, 27, ewb::MC_VM, false, 32, 4, 6>(p, mp, b, V, Pe, st);
+    }
+    return fail(EWB_ERR_UNSUPPORTED, "element/material combination not implemented");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ewb_last_error(void) { return g_err.c_str(); }
+int ewb_version(void) { return 100; }
+int64_t ewb_launch_count(void) { return g_launches; }
+
+int ewb_plan_create(ewb_plan** out, int el_type, int64_t n_el, int64_t n_node, const int32_t* conn_host, int device) {
+    if (!out || !conn_host || n_el <= 0 || n_node <= 0) return fail(EWB_ERR_ARG, "ewb_plan_create: bad arguments");
+    int nn, ngp;
+    if (int rc = elementInfo(el_type, &nn, &ngp)) return rc;
+    if (n_el * nn >= (int64_t)1 << 31) return fail(EWB_ERR_UNSUPPORTED, "too many element nodes for int32 incidence");
+    CUDA_TRY(cudaSetDevice(device));
+    auto* p = new ewb_plan();
+    p->device = device; p->elType = el_type; p->nn = nn; p->ngp = ngp; p->nEl = n_el; p->nNode = n_node;
+    p->connHost.assign(conn_host, conn_host + n_el * nn);
+    for (int64_t i = 0; i < n_el * nn; ++i)
+        if (conn_host[i] < 0 || conn_host[i] >= n_node) { delete p; return fail(EWB_ERR_ARG, "connectivity index out of range"); }
+
+    // node -> incident (element, local node), ascending element (counting sort)
+    std::vector<int64_t> incPtr(n_node + 1, 0);
+    for (int64_t i = 0; i < n_el * nn; ++i) incPtr[conn_host[i] + 1]++;
+    for (int64_t n = 0; n < n_node; ++n) incPtr[n + 1] += incPtr[n];
+    std::vector<int32_t> inc(incPtr[n_node]);
+    {
+        std::vector<int64_t> cur(incPtr.begin(), incPtr.end() - 1);
+        for (int64_t e = 0; e < n_el; ++e)
+            for (int a = 0; a < nn; ++a) inc[cur[conn_host[e * nn + a]]++] = (int32_t)(e * nn + a);
+    }
+    // node adjacency: sorted unique union of the nodes of all incident elements
+    std::vector<int64_t> adjPtr(n_node + 1, 0);
+    std::vector<std::vector<int32_t>> chunks;
+    const int64_t CH = 1 << 16;
+    const int64_t nChunks = (n_node + CH - 1) / CH;
+    chunks.resize(nChunks);
+#pragma omp parallel for schedule(dynamic)
+    for (int64_t c = 0; c < nChunks; ++c) {
+        std::vector<int32_t> tmp;
+        auto& outv = chunks[c];
+        for (int64_t n = c * CH; n < std::min(n_node, (c + 1) * CH); ++n) {
+            tmp.clear();
+            for (int64_t k = incPtr[n]; k < incPtr[n + 1]; ++k) {
+                const int64_t e = inc[k] / nn;
+                for (int a = 0; a < nn; ++a) tmp.push_back(conn_host[e * nn + a]);
+            }
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            adjPtr[n + 1] = (int64_t)tmp.size();
+            outv.insert(outv.end(), tmp.begin(), tmp.end());
+        }
+    }
+    for (int64_t n = 0; n < n_node; ++n) adjPtr[n + 1] += adjPtr[n];
+    std::vector<int32_t> adj;
+    adj.reserve(adjPtr[n_node]);
+    for (auto& c : chunks) { adj.insert(adj.end(), c.begin(), c.end()); std::vector<int32_t>().swap(c); }
+    p->nSlots = adjPtr[n_node];
+    p->nnz = 9 * p->nSlots;
+    if (p->nnz >= (int64_t)1 << 31) { delete p; return fail(EWB_ERR_UNSUPPORTED, "nnz exceeds int32 CSR indices (csrgenerator.pyx uses C int)"); }
+
+    int rc = EWB_OK;
+    if ((rc = upload(&p->conn, p->connHost)) || (rc = upload(&p->adjPtr, adjPtr)) || (rc = upload(&p->adj, adj)) ||
+        (rc = upload(&p->incPtr, incPtr)) || (rc = upload(&p->inc, inc))) {
+        ewb_plan_destroy(p);
+        return rc;
+    }
+    CUDA_TRY(cudaMalloc((void**)&p->failFlag, sizeof(int)));
+    CUDA_TRY(cudaMemset(p->failFlag, 0, sizeof(int)));
+    CUDA_TRY(cudaMallocHost((void**)&p->failHost, sizeof(int)));
+    *p->failHost = 0;
+    *out = p;
+    return EWB_OK;
+}
+
+void ewb_plan_destroy(ewb_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaFree(p->conn); cudaFree(p->adjPtr); cudaFree(p->adj); cudaFree(p->incPtr); cudaFree(p->inc);
+    cudaFree(p->failFlag); cudaFree(p->peScratch); cudaFree(p->vijScratch);
+    if (p->failHost) cudaFreeHost(p->failHost);
+    p->sweep.release();
+    delete p;
+}
+
+int64_t ewb_plan_nnz(const ewb_plan* p) { return p ? p->nnz : -1; }
+int64_t ewb_plan_ndof(const ewb_plan* p) { return p ? 3 * p->nNode : -1; }
+int ewb_plan_n_gauss(const ewb_plan* p) { return p ? p->ngp : -1; }
+int ewb_plan_n_el_dof(const ewb_plan* p) { return p ? 3 * p->nn : -1; }
+int ewb_plan_is_box(const ewb_plan* p) { return p && p->isBox ? 1 : 0; }
+
+}  // extern "C"
+
+namespace {
+
+__global__ void csrPatternKernel(int64_t nNode, const int64_t* __restrict__ adjPtr, const int32_t* __restrict__ adj, int32_t* __restrict__ indptr,
+                                 int32_t* __restrict__ indices) {
+    const int64_t A = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (A >= nNode) return;
+    const int64_t s0 = adjPtr[A], deg = adjPtr[A + 1] - s0, base = 9 * s0;
+    for (int i = 0; i < 3; ++i) {
+        indptr[3 * A + i] = (int32_t)(base + i * 3 * deg);
+        for (int64_t s = 0; s < deg; ++s) {
+            const int32_t B = adj[s0 + s];
+            for (int j = 0; j < 3; ++j) indices[base + i * 3 * deg + 3 * s + j] = 3 * B + j;
+        }
+    }
+    if (A == nNode - 1) indptr[3 * nNode] = (int32_t)(9 * adjPtr[nNode]);
+}
+
+// x[p] for COO pair p of element e: row = dof[p % n], col = dof[p / n]  (dofmanager.py:552-553, csrgenerator.pyx:82-98)
+__global__ void slotMapKernel(int nn, int64_t e0, int64_t e1, const int32_t* __restrict__ conn, const int64_t* __restrict__ adjPtr,
+                              const int32_t* __restrict__ adj, int32_t* __restrict__ x) {
+    const int nd = 3 * nn;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (e1 - e0) * nd * nd;
+    if (idx >= total) return;
+    const int64_t e = e0 + idx / (nd * nd);
+    const int p = (int)(idx % (nd * nd));
+    const int r = p % nd, c = p / nd;
+    const int32_t A = conn[e * nn + r / 3], B = conn[e * nn + c / 3];
+    const int64_t s0 = adjPtr[A], deg = adjPtr[A + 1] - s0;
+    int64_t lo = 0, hi = deg - 1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (adj[s0 + mid] < B) lo = mid + 1; else hi = mid;
+    }
+    x[idx] = (int32_t)(9 * s0 + (r % 3) * 3 * deg + 3 * lo + (c % 3));
+}
+
+__global__ void stateTransposeKernel(const double* __restrict__ src, double* __restrict__ dst, int64_t nEl, int nGp, int nState, int toSoa) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = nEl * nGp * nState;
+    if (idx >= total) return;
+    // idx enumerates the destination
+    if (toSoa) {  // dst[c][e][gp] = src[e][gp][c]
+        const int64_t c = idx / (nEl * nGp), r = idx % (nEl * nGp);
+        dst[idx] = src[r * nState + c];
+    } else {  // dst[e][gp][c] = src[c][e][gp]
+        const int64_t r = idx / nState, c = idx % nState;
+        dst[idx] = src[c * (nEl * nGp) + r];
+    }
+}
+
+__global__ void dirichletKernel(const int32_t* __restrict__ indptr3, const int64_t* __restrict__ adjPtr, const int32_t* __restrict__ adj,
+                                double* __restrict__ data, const int32_t* __restrict__ dofs, int64_t n) {
+    (void)indptr3;
+    const int64_t k = blockIdx.x;
+    if (k >= n) return;
+    const int32_t dof = dofs[k];
+    const int64_t A = dof / 3, i = dof % 3;
+    const int64_t s0 = adjPtr[A], deg = adjPtr[A + 1] - s0;
+    const int64_t row0 = 9 * s0 + i * 3 * deg;
+    for (int64_t q = threadIdx.x; q < 3 * deg; q += blockDim.x) {
+        const int32_t col = 3 * adj[s0 + q / 3] + (int32_t)(q % 3);
+        data[row0 + q] = (col == dof) ? 1.0 : 0.0;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ewb_plan_csr_pattern(const ewb_plan* p, int32_t* indptr_dev, int32_t* indices_dev, void* stream) {
+    if (!p || !indptr_dev || !indices_dev) return fail(EWB_ERR_ARG, "ewb_plan_csr_pattern: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const int B = 128;
+    csrPatternKernel<<<(unsigned)((p->nNode + B - 1) / B), B, 0, (cudaStream_t)stream>>>(p->nNode, p->adjPtr, p->adj, indptr_dev, indices_dev);
+    LAUNCH_CHECK();
+    return EWB_OK;
+}
+
+int ewb_plan_slot_map(const ewb_plan* p, int64_t e0, int64_t e1, int32_t* x_dev, void* stream) {
+    if (!p || !x_dev || e0 < 0 || e1 > p->nEl || e0 >= e1) return fail(EWB_ERR_ARG, "ewb_plan_slot_map: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const int nd = 3 * p->nn;
+    const int64_t total = (e1 - e0) * nd * nd;
+    const int B = 256;
+    slotMapKernel<<<(unsigned)((total + B - 1) / B), B, 0, (cudaStream_t)stream>>>(p->nn, e0, e1, p->conn, p->adjPtr, p->adj, x_dev);
+    LAUNCH_CHECK();
+    return EWB_OK;
+}
+
+int ewb_plan_set_box(ewb_plan* p, int64_t nX, int64_t nY, int64_t nZ) {
+    if (!p) return fail(EWB_ERR_ARG, "null plan");
+    if (p->nn != 8) return fail(EWB_ERR_UNSUPPORTED, "structured sweep implemented for 8-node hexahedra only");
+    if (nX * nY * nZ != p->nEl || (nX + 1) * (nY + 1) * (nZ + 1) != p->nNode) return fail(EWB_ERR_NOT_BOX, "box dimensions do not match the mesh");
+    // verify against the generator's closed form (generators/boxgen.py:133-141,168-185)
+    static const int off[8][3] = {{0, 0, 0}, {0, 0, 1}, {1, 0, 1}, {1, 0, 0}, {0, 1, 0}, {0, 1, 1}, {1, 1, 1}, {1, 1, 0}};
+    const int64_t NY = nY + 1, NZ = nZ + 1;
+    bool ok = true;
+#pragma omp parallel for reduction(&& : ok)
+    for (int64_t e = 0; e < p->nEl; ++e) {
+        const int64_t ix = e / (nY * nZ), iy = (e / nZ) % nY, iz = e % nZ;
+        for (int a = 0; a < 8; ++a) {
+            const int64_t n = (ix + off[a][0]) * NY * NZ + (iy + off[a][1]) * NZ + (iz + off[a][2]);
+            ok = ok && (p->connHost[e * 8 + a] == (int32_t)n);
+        }
+    }
+    if (!ok) return fail(EWB_ERR_NOT_BOX, "connectivity is not BoxGen-ordered");
+    p->isBox = true; p->nX = nX; p->nY = nY; p->nZ = nZ;
+    if (int rc = p->sweep.build(nX, nY, nZ)) return fail(rc, "sweep plan build failed");
+    return EWB_OK;
+}
+
+int ewb_compute_elements_vij(ewb_plan* p, int material, const double* props, int n_props, const ewb_buffers* b, double* pe_dev, int flags,
+                             void* stream) {
+    if (!p || !b || !props || !pe_dev) return fail(EWB_ERR_ARG, "ewb_compute_elements_vij: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    ewb::MatParams mp; int mc, nms;
+    if (int rc = materialClass(p->elType, material, props, n_props, &mp, &mc, &nms)) return rc;
+    double* V = (flags & EWB_FLAG_NO_STIFFNESS) ? nullptr : b->vij;
+    return dispatchVij(p, mc, mp, b, V, pe_dev, (cudaStream_t)stream);
+}
+
+int ewb_update_csr(ewb_plan* p, const double* vij_dev, double* csr_data_dev, void* stream) {
+    if (!p || !vij_dev || !csr_data_dev) return fail(EWB_ERR_ARG, "ewb_update_csr: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const int B = 128;
+    const unsigned grid = (unsigned)((p->nSlots + B - 1) / B);
+    if (p->nn == 8)
+        ewb::updateCsrKernel<8><<<grid, B, 0, (cudaStream_t)stream>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, vij_dev, csr_data_dev, p->nSlots);
+    else
+        ewb::updateCsrKernel<20><<<grid, B, 0, (cudaStream_t)stream>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, vij_dev, csr_data_dev, p->nSlots);
+    LAUNCH_CHECK();
+    return EWB_OK;
+}
+
+int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, const ewb_buffers* b, const double time[2], double dT, int flags,
+                 void* stream) {
+    (void)time; (void)dT;  // the scoped materials are rate independent (element.py:332 passes them through)
+    if (!p || !b || !props) return fail(EWB_ERR_ARG, "ewb_assemble: bad arguments");
+    if (!b->coords || !b->U || !b->dU || !b->state_ref || !b->state_temp || !b->P || !b->F) return fail(EWB_ERR_ARG, "ewb_assemble: null buffer");
+    const bool wantK = !(flags & EWB_FLAG_NO_STIFFNESS);
+    if (wantK && !b->csr_data) return fail(EWB_ERR_ARG, "ewb_assemble: csr_data is null");
+    CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ewb::MatParams mp; int mc, nms;
+    if (int rc = materialClass(p->elType, material, props, n_props, &mp, &mc, &nms)) return rc;
+
+    if (p->isBox && !(flags & EWB_FLAG_FORCE_GENERIC) && b->vij == nullptr) {
+        int launches = 0;
+        int rc = p->sweep.launch(p->elType, mc, mp, b, p->failFlag, flags, st, &launches);
+        g_launches += launches;
+        if (rc == EWB_OK) return EWB_OK;
+        if (rc != EWB_ERR_UNSUPPORTED) return fail(rc, std::string("sweep launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    }
+
+    // generic two-phase path
+    const int nd = 3 * p->nn;
+    if (!p->peScratch) CUDA_TRY(cudaMalloc((void**)&p->peScratch, (size_t)p->nEl * nd * sizeof(double)));
+    double* V = nullptr;
+    if (wantK) {
+        V = b->vij;
+        if (!V) {
+            if (!p->vijScratch) CUDA_TRY(cudaMalloc((void**)&p->vijScratch, (size_t)p->nEl * nd * nd * sizeof(double)));
+            V = p->vijScratch;
+        }
+    }
+    if (int rc = dispatchVij(p, mc, mp, b, V, p->peScratch, st)) return rc;
+    {
+        const int B = 256;
+        const unsigned grid = (unsigned)((3 * p->nNode + B - 1) / B);
+        const int acc = (flags & EWB_FLAG_ACCUMULATE_PF) ? 1 : 0;
+        if (p->nn == 8) ewb::gatherResidualKernel<8><<<grid, B, 0, st>>>(p->nNode, p->incPtr, p->inc, p->peScratch, b->P, b->F, acc);
+        else ewb::gatherResidualKernel<20><<<grid, B, 0, st>>>(p->nNode, p->incPtr, p->inc, p->peScratch, b->P, b->F, acc);
+        LAUNCH_CHECK();
+    }
+    if (wantK) return ewb_update_csr(p, V, b->csr_data, stream);
+    return EWB_OK;
+}
+
+int ewb_poll_status(ewb_plan* p, void* stream, double* pNewDT) {
+    if (!p) return fail(EWB_ERR_ARG, "null plan");
+    CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(p->failHost, p->failFlag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemsetAsync(p->failFlag, 0, sizeof(int), st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (*p->failHost & 1) {
+        if (pNewDT) *pNewDT = 0.5;
+        g_err = "Von Mises Newton failed.";
+        return EWB_CUTBACK;
+    }
+    if (pNewDT) *pNewDT = 1.0;
+    return EWB_OK;
+}
+
+int ewb_state_to_soa(const double* aos, double* soa, int64_t nEl, int nGp, int nState, void* stream) {
+    if (!aos || !soa) return fail(EWB_ERR_ARG, "null state buffer");
+    const int64_t total = nEl * nGp * nState;
+    stateTransposeKernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(aos, soa, nEl, nGp, nState, 1);
+    LAUNCH_CHECK();
+    return EWB_OK;
+}
+
+int ewb_state_to_aos(const double* soa, double* aos, int64_t nEl, int nGp, int nState, void* stream) {
+    if (!aos || !soa) return fail(EWB_ERR_ARG, "null state buffer");
+    const int64_t total = nEl * nGp * nState;
+    stateTransposeKernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(soa, aos, nEl, nGp, nState, 0);
+    LAUNCH_CHECK();
+    return EWB_OK;
+}
+
+int ewb_apply_dirichlet_k(const ewb_plan* p, double* data, const int32_t* dofs_dev, int64_t n, void* stream) {
+    if (!p || !data || (!dofs_dev && n > 0)) return fail(EWB_ERR_ARG, "ewb_apply_dirichlet_k: bad arguments");
+    if (n == 0) return EWB_OK;
+    CUDA_TRY(cudaSetDevice(p->device));
+    dirichletKernel<<<(unsigned)n, 96, 0, (cudaStream_t)stream>>>(nullptr, p->adjPtr, p->adj, data, dofs_dev, n);
+    LAUNCH_CHECK();
+    return EWB_OK;
+}
+
+}  // extern "C"

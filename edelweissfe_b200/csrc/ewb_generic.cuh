@@ -1,0 +1,118 @@
+// Generic (arbitrary connectivity) two-phase path — the device restatement of the reference's own
+// data flow:   NIST.computeElements  -> VIJ values + per-element Pe     (nonlinearimplicitstatic.py:794-849)
+//              CSRGenerator.updateCSR -> CSR data, summed in ascending COO order (csrgenerator.pyx:100-115)
+//              P[el] += Pe ; F[el] += |Pe| -> gathered per node in ascending element order (:843-844)
+// Deterministic (no atomics).  It materialises V like the reference does, so it moves ~3.5x the
+// algorithmic bytes; the fused BoxGen sweep (ewb_sweep.cuh) is the fast path.
+#pragma once
+#include "ewb_tile.cuh"
+
+namespace ewb {
+
+template <int NN>
+struct VijEmit {
+    static constexpr int ND = 3 * NN;
+    double* V;   // element slice [ND*ND] or nullptr
+    double* Pe;  // element slice [ND]
+    __device__ __forceinline__ void residual(int a, const double P[3]) const {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Pe[3 * a + i] = P[i];
+    }
+    __device__ __forceinline__ void block(int a, int b, const double K[9]) const {
+        if (V == nullptr) return;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) V[(3 * a + i) * ND + 3 * b + j] = K[i * 3 + j];
+    }
+};
+
+// T threads cooperate on one element (T >= NGP and T >= NN), E elements per CTA.
+template <int NN, int NGP, int MC, bool TL, int T, int E, int BLK>
+__global__ void __launch_bounds__(T* E) computeElementsVijKernel(int64_t nEl, const int32_t* __restrict__ conn, const double* __restrict__ coords,
+                                                                const double* __restrict__ U, const double* __restrict__ dU,
+                                                                const double* __restrict__ stateRef, double* __restrict__ stateTemp,
+                                                                double* __restrict__ V, double* __restrict__ Pe, MatParams mp, int* failFlag) {
+    using L = TileLayout<NN, NGP, MC>;
+    extern __shared__ double smem[];
+    const int el = threadIdx.x / T, t = threadIdx.x % T;
+    const int64_t e = (int64_t)blockIdx.x * E + el;
+    double* sm = smem + el * L::PER_EL;
+    const bool active = e < nEl;
+    if (active) stageNodes<NN, NGP, MC, T>(sm, conn + e * NN, coords, U, dU, t);
+    __syncthreads();
+    if (active && t < NGP) {
+        const int64_t cstride = nEl * NGP;
+        const int64_t off = e * NGP + t;
+        gaussPoint<NN, NGP, MC, TL>(sm, t, mp, stateRef + off, stateTemp + off, cstride, true, failFlag);
+    }
+    __syncthreads();
+    if (active && t < NN) {
+        VijEmit<NN> emit{V ? V + e * (int64_t)(9 * NN * NN) : nullptr, Pe + e * (3 * NN)};
+        nodeRow<NN, NGP, MC, BLK>(sm, t, mp, V != nullptr, emit);
+    }
+}
+
+// CSRGenerator.updateCSR as a gather: one thread per (node A, neighbour slot s) sums the 3x3 block
+// over the elements incident to A in ascending element order == ascending COO index.
+// Row of dof 3A+i starts at 9*adjPtr[A] + i*3*deg(A).
+template <int NN>
+__global__ void updateCsrKernel(int64_t nNode, const int64_t* __restrict__ adjPtr, const int32_t* __restrict__ adj,
+                                const int64_t* __restrict__ incPtr, const int32_t* __restrict__ inc, const int32_t* __restrict__ conn,
+                                const double* __restrict__ V, double* __restrict__ data, int64_t nSlots) {
+    constexpr int ND = 3 * NN;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nSlots) return;
+    // binary search the node owning global slot idx
+    int64_t lo = 0, hi = nNode;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (adjPtr[mid] <= idx) lo = mid; else hi = mid;
+    }
+    const int64_t A = lo;
+    const int64_t s = idx - adjPtr[A];
+    const int64_t deg = adjPtr[A + 1] - adjPtr[A];
+    const int32_t B = adj[idx];
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t k = incPtr[A]; k < incPtr[A + 1]; ++k) {
+        const int32_t ea = inc[k];
+        const int64_t e = ea / NN;
+        const int a = ea % NN;
+        int b = -1;
+        for (int q = 0; q < NN; ++q)
+            if (conn[e * NN + q] == B) { b = q; break; }
+        if (b < 0) continue;
+        // row dof = dof[p % n] = 3a+i, col dof = dof[p / n] = 3b+j  ->  p = (3b+j)*n + 3a+i   (dofmanager.py:552-553)
+        const double* Ve = V + e * (int64_t)(ND * ND);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc[i * 3 + j] += Ve[(3 * b + j) * ND + 3 * a + i];
+    }
+    const int64_t base = 9 * adjPtr[A];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) data[base + i * 3 * deg + 3 * s + j] = acc[i * 3 + j];
+}
+
+// P[el] += Pe ; F[el] += |Pe| : per node, ascending element order.
+template <int NN>
+__global__ void gatherResidualKernel(int64_t nNode, const int64_t* __restrict__ incPtr, const int32_t* __restrict__ inc,
+                                     const double* __restrict__ Pe, double* __restrict__ P, double* __restrict__ F, int accumulate) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 3 * nNode) return;
+    const int64_t A = idx / 3;
+    const int c = idx % 3;
+    double p = accumulate ? P[idx] : 0.0, f = accumulate ? F[idx] : 0.0;
+    for (int64_t k = incPtr[A]; k < incPtr[A + 1]; ++k) {
+        const int32_t ea = inc[k];
+        const double v = Pe[(int64_t)(ea / NN) * (3 * NN) + 3 * (ea % NN) + c];
+        p += v;
+        f += fabs(v);
+    }
+    P[idx] = p;
+    F[idx] = f;
+}
+
+}  // namespace ewb

@@ -1,0 +1,129 @@
+/*
+ * edelweiss_b200.h — C ABI of the B200-native element-loop / CSR-assembly path.
+ *
+ * This is the drop-in boundary for EdelweissFE's hot path.  Every entry
+ * point names the reference interface it replaces (paths relative to the reference tree,
+ * edelweissfe/...).  Plain pointers and sizes only; device pointers are raw CUDA device
+ * addresses (e.g. torch.Tensor.data_ptr()), owned by the caller for the duration of a call.
+ *
+ * Conventions shared with the reference:
+ *   - dof(node i, component c) = 3*i + c, i = position of the node in model.nodes order
+ *     (numerics/dofmanager.py:280-292, 445-471);
+ *   - element dof list is node-major (element.py:116-121 dofIndicesPermutation = identity);
+ *   - CSR pattern = SciPy-canonical union pattern, int32 indptr/indices, explicit zeros kept
+ *     (numerics/csrgenerator.pyx:68-77);
+ *   - Ke is written row-major into the element's VIJ slice whose (I,J) are column-major, i.e.
+ *     K_global[dof[j], dof[i]] += Ke[i][j] (numerics/dofmanager.py:543-555, element.py:318);
+ *   - P -= Bt sigma detJ w (element.py:344); F accumulates |Pe| (nonlinearimplicitstatic.py:844).
+ *
+ * Gauss-point state on the device is component-major SoA:  state[c][e][gp]
+ * (c < 12 + nMaterialState), the transposition of the reference's per-element
+ * _stateVarsRef[gp][c] (element.py:225-236).  ewb_state_to_soa / ewb_state_to_aos convert.
+ */
+#ifndef EDELWEISS_B200_H
+#define EDELWEISS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element formulations (provider "edelweiss"; elements/library.py:212-227, 260-275, 453-468) */
+enum { EWB_C3D8 = 0, EWB_C3D20 = 1, EWB_C3D8TL = 2 };
+
+/* materials (materials/linearelastic, materials/vonmises, materials/neohooke) */
+enum {
+    EWB_MAT_LINEARELASTIC = 0, /* props: E, nu                               (linearelastic.py:185-210) */
+    EWB_MAT_VONMISES = 1,      /* props: E, nu, fy0, HLin, dfy, delta        (vonmises.py:186-254)      */
+    EWB_MAT_NEOHOOKE_WA = 2,   /* props: mu, K                 (neohookepencegouformulationa.py:107-141) */
+    EWB_MAT_NEOHOOKE_WB = 3,   /*                              (neohookepencegouformulationb.py:130-145) */
+    EWB_MAT_NEOHOOKE_WC = 4    /*                              (neohookepencegouformulationc.py:130-143) */
+};
+
+/* status codes */
+enum {
+    EWB_OK = 0,
+    EWB_CUTBACK = 1,       /* a material asked for a smaller increment; *pNewDT holds the factor.
+                              Mirrors CutbackRequest("Von Mises Newton failed.", 0.5), vonmises.py:230-231,
+                              and the pNewDT convention of marmotelement/element.pxd:97-103. */
+    EWB_ERR_ARG = -1,
+    EWB_ERR_CUDA = -2,
+    EWB_ERR_UNSUPPORTED = -3,
+    EWB_ERR_NOT_BOX = -4
+};
+
+/* assembly flags */
+enum {
+    EWB_FLAG_ACCUMULATE_PF = 1, /* P += , F += (reference semantics on a caller-zeroed vector); default overwrites */
+    EWB_FLAG_FORCE_GENERIC = 2, /* use the two-phase VIJ path even when a structured (BoxGen) plan exists */
+    EWB_FLAG_NO_STIFFNESS = 4   /* residual / state only (P, F, stateTemp) */
+};
+
+typedef struct ewb_plan ewb_plan; /* opaque: mesh topology + CSR slot tables on one device */
+
+/* Device buffers of one assembly call.  All pointers are device addresses. */
+typedef struct ewb_buffers {
+    const double* coords;    /* [nNode][3]                     Node.coordinates                          */
+    const double* U;         /* [nDof]   U_np                  nonlinearimplicitstatic.py:416             */
+    const double* dU;        /* [nDof]   dU                    nonlinearimplicitstatic.py:417             */
+    const double* state_ref; /* [nState][nEl][nGp]  last accepted state (element.py:320 copies it)        */
+    double* state_temp;      /* [nState][nEl][nGp]  updated state (element.py:346), committed by the caller */
+    double* csr_data;        /* [nnz]    overwritten: CSRGenerator.updateCSR (csrgenerator.pyx:100-115)    */
+    double* P;               /* [nDof]   reaction vector                                                   */
+    double* F;               /* [nDof]   accumulated |flux|                                                */
+    double* vij;             /* optional [nEl*nDofEl^2]: VIJSystemMatrix values, reference layout, or NULL */
+} ewb_buffers;
+
+const char* ewb_last_error(void);
+int ewb_version(void);
+
+/* ---- topology / pattern -------------------------------------------------------------------
+ * Replaces DofManager._locateNodeCouplingEntitiesInDofVector + _initializeVIJPattern
+ * (numerics/dofmanager.py:445-471, 522-557) and CSRGenerator.__init__ (csrgenerator.pyx:47-98).
+ * conn_host: HOST int32 [nEl][nNodesPerElement], 0-based node positions. */
+int ewb_plan_create(ewb_plan** plan, int el_type, int64_t n_el, int64_t n_node, const int32_t* conn_host, int device);
+void ewb_plan_destroy(ewb_plan* plan);
+int64_t ewb_plan_nnz(const ewb_plan* plan);
+int64_t ewb_plan_ndof(const ewb_plan* plan);
+int ewb_plan_n_gauss(const ewb_plan* plan);
+int ewb_plan_n_el_dof(const ewb_plan* plan);
+/* CSR pattern into caller-owned device buffers: indptr int32[nDof+1], indices int32[nnz]. */
+int ewb_plan_csr_pattern(const ewb_plan* plan, int32_t* indptr_dev, int32_t* indices_dev, void* stream);
+/* COO->CSR slot map x (csrgenerator.pyx:82-98) for elements [e0,e1): int32[(e1-e0)*nDofEl^2], device. */
+int ewb_plan_slot_map(const ewb_plan* plan, int64_t e0, int64_t e1, int32_t* x_dev, void* stream);
+/* Declare the mesh a BoxGen Hexa8 box (generators/boxgen.py:124-185) of nX x nY x nZ elements.
+ * The connectivity is verified against the generator's closed form; enables the fused sweep kernel. */
+int ewb_plan_set_box(ewb_plan* plan, int64_t nX, int64_t nY, int64_t nZ);
+int ewb_plan_is_box(const ewb_plan* plan);
+
+/* ---- the hot path ---------------------------------------------------------------------------
+ * One NIST.computeElements pass + CSRGenerator.updateCSR on the device
+ * (solvers/nonlinearimplicitstatic.py:794-849, 753-769).  Asynchronous on `stream`. */
+int ewb_assemble(ewb_plan* plan, int material, const double* props_host, int n_props, const ewb_buffers* buf,
+                 const double time[2], double dT, int flags, void* stream);
+/* Synchronises `stream`, returns EWB_OK or EWB_CUTBACK (then *pNewDT = 0.5). */
+int ewb_poll_status(ewb_plan* plan, void* stream, double* pNewDT);
+
+/* ---- pieces of the reference-faithful two-phase path (exposed for parity tests) -------------- */
+/* computeElements only: V (VIJ values), Pe (per-element residual [nEl][nDofEl]), stateTemp. */
+int ewb_compute_elements_vij(ewb_plan* plan, int material, const double* props_host, int n_props,
+                             const ewb_buffers* buf, double* pe_dev, int flags, void* stream);
+/* CSRGenerator.updateCSR: data[x[p]] += V[p], summed in ascending p (deterministic gather). */
+int ewb_update_csr(ewb_plan* plan, const double* vij_dev, double* csr_data_dev, void* stream);
+
+/* ---- state layout helpers (element.py:225-236 <-> device SoA) ------------------------------- */
+int ewb_state_to_soa(const double* aos_dev, double* soa_dev, int64_t n_el, int n_gp, int n_state, void* stream);
+int ewb_state_to_aos(const double* soa_dev, double* aos_dev, int64_t n_el, int n_gp, int n_state, void* stream);
+
+/* ---- NISTParallel.applyDirichletK (nonlinearimplicitstaticparallelmk2.pyx:66-109):
+ * zero the CSR rows of the given dofs and put 1 on their diagonal (pattern unchanged). */
+int ewb_apply_dirichlet_k(const ewb_plan* plan, double* csr_data_dev, const int32_t* dofs_dev, int64_t n, void* stream);
+
+/* number of this library's kernel launches since load (bench.py's gpu_launches) */
+int64_t ewb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDELWEISS_B200_H */
