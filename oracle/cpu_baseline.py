@@ -1,0 +1,60 @@
+"""CPU baseline leg of bench.py (TEST/BENCH INFRASTRUCTURE, not product): times the oracle —
+the CPU restatement of the reference's element loop + updateCSR — on a bounded BoxGen sample of
+the bench workload.  Uses the C/OpenMP restatement (oracle/element_loop.c) when it has been built,
+else the NumPy port.  kind is always "port": the reference itself is Python and cannot travel."""
+import os
+import time
+
+import numpy as np
+
+from . import port
+
+_WL = {
+    "boxgen100_c3d8_linearelastic": ("C3D8", "linearelastic", [2.1e4, 0.22], 1e-3),
+    "boxgen200x100x100_c3d8_vonmises": ("C3D8", "vonmises", [2.1e4, 0.22, 355.0, 1000.0, 200.0, 1400.0], 5e-3),
+    "boxgen100_c3d8tl_neohookewa": ("C3D8TL", "neohookewa", [91304.34783, 100000.0], 1e-2),
+    "boxgen100x100x50_c3d20_linearelastic": ("C3D20", "linearelastic", [2.1e4, 0.22], 1e-3),
+}
+
+
+def run(workload, sample_n, steps=1, warmup=0):
+    elType, material, props, scale = _WL[workload]
+    nn = 20 if "20" in elType else 8
+    if nn == 20:
+        sample_n = max(4, sample_n // 3)
+    n = sample_n
+    coords, conn = port.boxgen(n, n, n, float(n), float(n), float(n), nnodes=nn)
+    rng = np.random.default_rng(0)
+    dU = scale * rng.standard_normal(3 * coords.shape[0])
+    nGp = 27 if nn == 20 else 8
+    state = np.zeros((conn.shape[0], nGp, 12 + port.MATERIAL_NSTATE[material]))
+    try:
+        from . import cport
+
+        impl = cport.load()
+    except Exception:
+        impl = None
+    if impl is not None and impl.supports(elType, material):
+        runner = impl.make_runner(elType, material, props, coords, conn, dU, dU, state)
+        cores, kind_note = impl.threads(), "C/OpenMP restatement of the reference algorithm (oracle/element_loop.c)"
+    else:
+        # pattern once (reference: per step), then the loop body per timed step
+        dofs = port.element_dofs(conn)
+        I, J = port.vij_pattern(dofs)  # noqa: E741
+        indptr, indices, x = port.csr_pattern(I, J, 3 * coords.shape[0])
+
+        def runner():
+            Ke, Pe, st, failed = port.compute_elements(elType, material, props, coords, conn, dU, dU, state)
+            port.update_csr(x, Ke.reshape(-1), indices.size)
+            np.bincount(dofs.reshape(-1), weights=Pe.reshape(-1), minlength=3 * coords.shape[0])
+
+        cores, kind_note = 1, "NumPy restatement (oracle/port.py), batched einsum"
+    for _ in range(warmup):
+        runner()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        runner()
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=conn.shape[0] / dt / 1e6, ms_per_step=dt * 1e3, cores=cores, kind="port", steps=steps, warmup=warmup,
+                sample=f"BoxGen {n}x{n}x{n} {elType} {material} ({conn.shape[0]} elements), one computeElements+updateCSR pass; {kind_note}; "
+                       f"host has {os.cpu_count()} logical cores")
