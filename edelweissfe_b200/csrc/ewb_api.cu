@@ -331,6 +331,7 @@ int ewb_plan_set_box(ewb_plan* p, int64_t nX, int64_t nY, int64_t nZ) {
     if (!ok) return fail(EWB_ERR_NOT_BOX, "connectivity is not BoxGen-ordered");
     p->isBox = true; p->nX = nX; p->nY = nY; p->nZ = nZ;
     if (int rc = p->sweep.build(nX, nY, nZ)) return fail(rc, "sweep plan build failed");
+    p->sweep.adjPtr = p->adjPtr;
     return EWB_OK;
 }
 

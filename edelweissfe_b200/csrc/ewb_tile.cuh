@@ -67,13 +67,13 @@ __device__ __forceinline__ void stageNodes(double* sm, const int32_t* __restrict
 // phase A
 // ---------------------------------------------------------------------------------------------
 // state_ref / state_temp point at component 0 of (element e, this gp); cstride = nEl * NGP.
-template <int NN, int NGP, int MC, bool TL>
-__device__ __forceinline__ void gaussPoint(double* sm, int gp, const MatParams& mp, const double* __restrict__ state_ref,
-                                           double* __restrict__ state_temp, int64_t cstride, bool writeState, int* failFlag) {
-    using L = TileLayout<NN, NGP, MC>;
-    const double* X = sm + L::OFF_X;
-    const double* dUe = sm + L::OFF_X + 3 * NN;
-    const double* Ue = sm + L::OFF_X + 6 * NN;
+// L: shared-memory layout (GST, NCO, OFF_G, OFF_Q, OFF_CO, HASQ, and the CO slot indices C_*).
+// X: nodal coordinates [NN][3]; uu: nodal dU (small strain) or U (TL) [NN][3] — shared memory or
+// registers (all indices are compile-time after unrolling).
+template <class L, int NN, int NGP, int MC, bool TL>
+__device__ __forceinline__ void gaussPointL(double* sm, const double* X, const double* uu, int gp, const MatParams& mp,
+                                            const double* __restrict__ state_ref, double* __restrict__ state_temp, int64_t cstride,
+                                            bool writeState, int* failFlag) {
     double* G = sm + L::OFF_G + gp * L::GST;
     double* CO = sm + L::OFF_CO + gp * L::NCO;
 
@@ -97,7 +97,6 @@ __device__ __forceinline__ void gaussPoint(double* sm, int gp, const MatParams& 
 
     // grad N_a = J^-1 dN_a ; displacement(-increment) gradient H[i][c] = sum_a u_a[i] g_a[c]
     double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const double* uu = TL ? Ue : dUe;
     forNodes<NN>([&](auto ic) {
         constexpr int a = decltype(ic)::value;
         double d[3], g[3];
@@ -132,13 +131,19 @@ __device__ __forceinline__ void gaussPoint(double* sm, int gp, const MatParams& 
             CO[0] = wd * r.lam;
             CO[1] = wd * r.mu;
             CO[2] = -wd * r.a;
+            if constexpr (L::NCO >= 16) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) CO[10 + i] = r.n[i];
+            }
             // p_a = B_a^T n = N g_a, N = tensor(n)  (n Voigt 11,22,33,12,13,23)
-            double* Q = sm + L::OFF_Q + gp * L::GST;
-            for (int a = 0; a < NN; ++a) {
-                const double gx = G[a * 3], gy = G[a * 3 + 1], gz = G[a * 3 + 2];
-                Q[a * 3 + 0] = r.n[0] * gx + r.n[3] * gy + r.n[4] * gz;
-                Q[a * 3 + 1] = r.n[3] * gx + r.n[1] * gy + r.n[5] * gz;
-                Q[a * 3 + 2] = r.n[4] * gx + r.n[5] * gy + r.n[2] * gz;
+            if constexpr (L::HASQ) {
+                double* Q = sm + L::OFF_Q + gp * L::GST;
+                for (int a = 0; a < NN; ++a) {
+                    const double gx = G[a * 3], gy = G[a * 3 + 1], gz = G[a * 3 + 2];
+                    Q[a * 3 + 0] = r.n[0] * gx + r.n[3] * gy + r.n[4] * gz;
+                    Q[a * 3 + 1] = r.n[3] * gx + r.n[1] * gy + r.n[5] * gz;
+                    Q[a * 3 + 2] = r.n[4] * gx + r.n[5] * gy + r.n[2] * gz;
+                }
             }
         }
         // -w detJ * stress as a tensor (xx,yy,zz,xy,xz,yz): Voigt 3,4,5 = 12,13,23
@@ -169,12 +174,18 @@ __device__ __forceinline__ void gaussPoint(double* sm, int gp, const MatParams& 
         for (int i = 0; i < 6; ++i) CO[4 + i] = -wd * r.tau[i];
 #pragma unroll
         for (int i = 0; i < 9; ++i) CO[10 + i] = F[i];
-        // n_a[m] = sum_j g_a[j] Finv[j][m]
-        double* Q = sm + L::OFF_Q + gp * L::GST;
-        for (int a = 0; a < NN; ++a) {
-            const double gx = G[a * 3], gy = G[a * 3 + 1], gz = G[a * 3 + 2];
+        if constexpr (L::NCO >= 28) {
 #pragma unroll
-            for (int m = 0; m < 3; ++m) Q[a * 3 + m] = gx * iF[m] + gy * iF[3 + m] + gz * iF[6 + m];
+            for (int i = 0; i < 9; ++i) CO[19 + i] = iF[i];
+        }
+        // n_a[m] = sum_j g_a[j] Finv[j][m]
+        if constexpr (L::HASQ) {
+            double* Q = sm + L::OFF_Q + gp * L::GST;
+            for (int a = 0; a < NN; ++a) {
+                const double gx = G[a * 3], gy = G[a * 3 + 1], gz = G[a * 3 + 2];
+#pragma unroll
+                for (int m = 0; m < 3; ++m) Q[a * 3 + m] = gx * iF[m] + gy * iF[3 + m] + gz * iF[6 + m];
+            }
         }
         // Green-Lagrange E = (H + H^T + H^T H)/2, Voigt strain 11,22,33,2*12,2*23,2*13 (voigtnotation.py:32-52)
         double E[6];
@@ -202,6 +213,15 @@ __device__ __forceinline__ void gaussPoint(double* sm, int gp, const MatParams& 
 #pragma unroll
         for (int c = 0; c < 12 + (MC != MC_LE ? 1 : 0); ++c) state_temp[c * cstride] = st[c];
     }
+}
+
+template <int NN, int NGP, int MC, bool TL>
+__device__ __forceinline__ void gaussPoint(double* sm, int gp, const MatParams& mp, const double* __restrict__ state_ref,
+                                           double* __restrict__ state_temp, int64_t cstride, bool writeState, int* failFlag) {
+    using L = TileLayout<NN, NGP, MC>;
+    const double* X = sm + L::OFF_X;
+    const double* uu = sm + L::OFF_X + (TL ? 6 * NN : 3 * NN);
+    gaussPointL<L, NN, NGP, MC, TL>(sm, X, uu, gp, mp, state_ref, state_temp, cstride, writeState, failFlag);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -63,6 +63,10 @@ def test_golden(name, path):
         ("C3D8", "linearelastic", [2.1e4, 0.22], (7, 9, 11), 1e-3),
         ("C3D8", "vonmises", [2.1e4, 0.22, 355, 1000, 200, 1400], (9, 8, 7), 5e-3),
         ("C3D8TL", "neohookewa", [91304.34783, 100000.0], (6, 7, 8), 2e-2),
+        ("C3D8", "linearelastic", [2.1e4, 0.22], (25, 16, 9), 1e-3),  # several x-chunks and y/z tiles, ragged last tiles
+        ("C3D8", "vonmises", [2.1e4, 0.22, 355, 1000, 200, 1400], (26, 8, 15), 5e-3),
+        ("C3D8TL", "neohookewb", [91304.34783, 100000.0], (5, 8, 7), 2e-2),
+        ("C3D8TL", "neohookewc", [91304.34783, 100000.0], (24, 7, 6), 2e-2),
         ("C3D20", "linearelastic", [2.1e4, 0.22], (3, 4, 3), 1e-3),
         ("C3D20", "vonmises", [2.1e4, 0.22, 355, 1000, 200, 1400], (3, 3, 4), 5e-3),
     ],
