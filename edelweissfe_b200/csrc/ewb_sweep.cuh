@@ -61,23 +61,323 @@ __device__ __forceinline__ int ndx(int a) { return (a >> 1) & 1; }
 __device__ __forceinline__ int ndy(int a) { return (a >> 2) & 1; }
 __device__ __forceinline__ int ndz(int a) { return (a ^ (a >> 1)) & 1; }
 
+// Phase B for ONE element by one warp: lane (r = lane>>2, q = lane&3) ends with the 3x3 stiffness blocks
+// K0 = K[node r][node 2q], K1 = K[node r][node 2q+1] and (all 4 lanes of r) the residual row Pr of node r.
+// T: the element's shared-memory tables written by phase A.
+template <int MC>
+__device__ __forceinline__ void elementBlocks(const double* T, int lane, const MatParams& mp, bool wantK, double (&K0)[9], double (&K1)[9],
+                                              double (&Pr)[3]) {
+    using L = SweepLayout<MC>;
+    const int r = lane >> 2, q = lane & 3;
+    double g[2][3];
+    Pr[0] = Pr[1] = Pr[2] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) g[ks][c] = T[L::OFF_G + (4 * ks + q) * L::GST + r * 3 + c];
+    // residual row partial: (-w detJ S) v_r over this lane's two Gauss points
+    if constexpr (MC == MC_LE) {
+        double c[3][3][2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const double* co = T + L::OFF_CO + (4 * ks + q) * L::NCO;
+            const double w = co[0];
+            const double* S = co + 4;
+            Pr[0] += S[0] * g[ks][0] + S[3] * g[ks][1] + S[4] * g[ks][2];
+            Pr[1] += S[3] * g[ks][0] + S[1] * g[ks][1] + S[5] * g[ks][2];
+            Pr[2] += S[4] * g[ks][0] + S[5] * g[ks][1] + S[2] * g[ks][2];
+            if (wantK) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double ai = w * g[ks][i];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) dmma(c[i][j], ai, g[ks][j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            double* Kt = t ? K1 : K0;
+            const double tr = mp.G * (c[0][0][t] + c[1][1][t] + c[2][2][t]);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = mp.lambda * c[i][j][t] + mp.G * c[j][i][t] + (i == j ? tr : 0.0);
+        }
+    } else if constexpr (MC == MC_VM) {
+        double c1[3][3][2], c2[3][3][2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) c1[i][j][0] = c1[i][j][1] = c2[i][j][0] = c2[i][j][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const double* co = T + L::OFF_CO + (4 * ks + q) * L::NCO;
+            const double cl = co[0], cm = co[1], ca = co[2];
+            const double* S = co + 4;
+            const double* n = co + 10;
+            Pr[0] += S[0] * g[ks][0] + S[3] * g[ks][1] + S[4] * g[ks][2];
+            Pr[1] += S[3] * g[ks][0] + S[1] * g[ks][1] + S[5] * g[ks][2];
+            Pr[2] += S[4] * g[ks][0] + S[5] * g[ks][1] + S[2] * g[ks][2];
+            if (wantK) {
+                double pv[3];
+                pv[0] = n[0] * g[ks][0] + n[3] * g[ks][1] + n[4] * g[ks][2];
+                pv[1] = n[3] * g[ks][0] + n[1] * g[ks][1] + n[5] * g[ks][2];
+                pv[2] = n[4] * g[ks][0] + n[5] * g[ks][1] + n[2] * g[ks][2];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double li = cl * g[ks][i], mi = cm * g[ks][i], ri = ca * pv[i];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        dmma(c1[i][j], li, g[ks][j]);
+                        dmma(c1[i][j], ri, pv[j]);
+                        dmma(c2[i][j], mi, g[ks][j]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            double* Kt = t ? K1 : K0;
+            const double tr = c2[0][0][t] + c2[1][1][t] + c2[2][2][t];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = c1[i][j][t] + c2[j][i][t] + (i == j ? tr : 0.0);
+        }
+    } else {
+        double c1[3][3][2], c2[3][3][2], d0[3][2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            d0[i][0] = d0[i][1] = 0.0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) c1[i][j][0] = c1[i][j][1] = c2[i][j][0] = c2[i][j][1] = 0.0;
+        }
+        const bool wb = (mp.kind == EWB_MAT_NEOHOOKE_WB);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const double* co = T + L::OFF_CO + (4 * ks + q) * L::NCO;
+            const double k0 = co[0], k1 = co[1], k2 = co[2], k4 = co[3];
+            const double* S = co + 4;
+            const double* F = co + 10;
+            const double* iF = co + 19;
+            double nv[3];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) nv[m] = g[ks][0] * iF[m] + g[ks][1] * iF[3 + m] + g[ks][2] * iF[6 + m];
+            Pr[0] += S[0] * nv[0] + S[3] * nv[1] + S[4] * nv[2];
+            Pr[1] += S[3] * nv[0] + S[1] * nv[1] + S[5] * nv[2];
+            Pr[2] += S[4] * nv[0] + S[5] * nv[1] + S[2] * nv[2];
+            if (wantK) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double a1 = k1 * nv[i], a2 = k2 * nv[i];
+                    dmma(d0[i], k0 * g[ks][i], g[ks][i]);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        dmma(c1[i][j], a1, nv[j]);
+                        dmma(c2[i][j], a2, nv[j]);
+                    }
+                }
+                if (wb) {  // W_b: + c4 (f_a n_b^T + n_a f_b^T), f = F g
+                    double fv[3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) fv[i] = F[i * 3] * g[ks][0] + F[i * 3 + 1] * g[ks][1] + F[i * 3 + 2] * g[ks][2];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            dmma(c1[i][j], k4 * fv[i], nv[j]);
+                            dmma(c1[i][j], k4 * nv[i], fv[j]);
+                        }
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            double* Kt = t ? K1 : K0;
+            const double tr = d0[0][t] + d0[1][t] + d0[2][t];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = c1[i][j][t] + c2[j][i][t] + (i == j ? tr : 0.0);
+        }
+    }
+    // reduce the residual row over the 4 lanes (Gauss-point pairs) of node r
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        Pr[i] += __shfl_xor_sync(0xffffffffu, Pr[i], 1);
+        Pr[i] += __shfl_xor_sync(0xffffffffu, Pr[i], 2);
+    }}
+
+// Phase A for Hexa8 with TWO lanes per (element, Gauss point): lane half h handles the nodes
+// a = a' + 4h (a' = 0..3; the two xi-faces of the element), partial J and displacement gradients are
+// combined with one butterfly shuffle.  Halves the registers per thread (so that 16 warps fit) and the
+// number of elements a warp has in flight (2), at the price of a redundant 3x3 inverse + material update.
+template <class L, int MC, bool TL>
+__device__ __forceinline__ void gaussPointHalf(double* sm, const double (&Xh)[12], const double (&uh)[12], int gp, int h, unsigned mask,
+                                               const MatParams& mp, const double* __restrict__ state_ref, double* __restrict__ state_temp,
+                                               int64_t cstride, bool writeState, int* failFlag) {
+    double* G = sm + L::OFF_G + gp * L::GST + 12 * h;
+    double* CO = sm + L::OFF_CO + gp * L::NCO;
+    constexpr int NST = 12 + (MC != MC_LE ? 1 : 0);
+    double st[13];
+#pragma unroll
+    for (int c = 0; c < NST; ++c) st[c] = state_ref[c * cstride];
+
+    double xi, eta, zeta, w;
+    Gauss<8>::get(gp, xi, eta, zeta, w);
+    const double sx = h ? 1.0 : -1.0;
+    const double fx = 1.0 + sx * xi;
+    double dN[4][3];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const double be = NodeLC<8>::eta(a), cz = NodeLC<8>::zeta(a);  // eta/zeta signs do not depend on h
+        const double fe = 1.0 + be * eta, fz = 1.0 + cz * zeta;
+        dN[a][0] = 0.125 * be * fx * fz;
+        dN[a][1] = 0.125 * sx * fe * fz;
+        dN[a][2] = 0.125 * cz * fx * fe;
+    }
+    double Jm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Jm[r * 3 + c] = fma(dN[a][r], Xh[a * 3 + c], Jm[r * 3 + c]);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Jm[i] += __shfl_xor_sync(mask, Jm[i], 1);
+    const double detJ = det3(Jm);
+    double iJ[9];
+    inv3(Jm, detJ, iJ);
+    const double wd = w * detJ;
+    double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        double g[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) g[c] = iJ[c * 3 + 0] * dN[a][0] + iJ[c * 3 + 1] * dN[a][1] + iJ[c * 3 + 2] * dN[a][2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) G[a * 3 + c] = g[c];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) H[i * 3 + c] = fma(uh[a * 3 + i], g[c], H[i * 3 + c]);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) H[i] += __shfl_xor_sync(mask, H[i], 1);
+
+    // both half-lanes run the (cheap) constitutive update; lane h == 0 publishes it
+    if constexpr (!TL) {
+        const double de[6] = {H[0], H[4], H[8], H[1] + H[3], H[2] + H[6], H[5] + H[7]};
+        double sg[6] = {st[0], st[1], st[2], st[3], st[4], st[5]};
+        if constexpr (MC == MC_LE) {
+            hookeAdd(mp, de, sg);
+            if (h == 0) CO[0] = wd;
+        } else {
+            VMResult r;
+            double kappa = st[12];
+            vonMises(mp, de, sg, kappa, r);
+            st[12] = kappa;
+            if (h == 0) {
+                if (r.failed) atomicOr(failFlag, 1);
+                CO[0] = wd * r.lam;
+                CO[1] = wd * r.mu;
+                CO[2] = -wd * r.a;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) CO[10 + i] = r.n[i];
+            }
+        }
+        if (h == 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) CO[4 + i] = -wd * sg[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            st[i] = sg[i];
+            st[6 + i] += de[i];
+        }
+    } else {
+        double F[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) F[i] = H[i];
+        F[0] += 1.0;
+        F[4] += 1.0;
+        F[8] += 1.0;
+        const double Jf = det3(F);
+        double iF[9];
+        inv3(F, Jf, iF);
+        NHResult r;
+        neoHooke(mp, F, Jf, r);
+        if (h == 0) {
+            CO[0] = wd * r.c0;
+            CO[1] = wd * r.c1;
+            CO[2] = wd * r.c2;
+            CO[3] = wd * r.c4;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) CO[4 + i] = -wd * r.tau[i];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) CO[10 + i] = F[i];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) CO[19 + i] = iF[i];
+        }
+        st[0] = r.tau[0];
+        st[1] = r.tau[1];
+        st[2] = r.tau[2];
+        st[3] = r.tau[3];
+        st[4] = r.tau[5];
+        st[5] = r.tau[4];
+        st[6] = H[0] + 0.5 * (H[0] * H[0] + H[3] * H[3] + H[6] * H[6]);
+        st[7] = H[4] + 0.5 * (H[1] * H[1] + H[4] * H[4] + H[7] * H[7]);
+        st[8] = H[8] + 0.5 * (H[2] * H[2] + H[5] * H[5] + H[8] * H[8]);
+        st[9] = H[1] + H[3] + H[0] * H[1] + H[3] * H[4] + H[6] * H[7];
+        st[10] = H[5] + H[7] + H[1] * H[2] + H[4] * H[5] + H[7] * H[8];
+        st[11] = H[2] + H[6] + H[0] * H[2] + H[3] * H[5] + H[6] * H[8];
+        st[12] = r.energy;
+    }
+    if (writeState && h == 0) {
+#pragma unroll
+        for (int c = 0; c < NST; ++c) state_temp[c * cstride] = st[c];
+    }
+}
+
+// Accumulator geometry (doubles): per node column CS, 4 segments, offsets chosen for few bank conflicts.
+template <int TY, int TZ>
+struct AccLayout {
+    static constexpr int NCOL = TY * TZ;
+    static constexpr int CS = 81;                 // [i][s9][j]: row i of a segment = 27 contiguous doubles
+    static constexpr int SEG = NCOL * CS + 7;     // 49*81+7 == 8 (mod 16)
+    static constexpr int OFF_0A = 0, OFF_0B = SEG, OFF_P = 2 * SEG, OFF_M = 3 * SEG;
+    static constexpr int PF = 4 * SEG;            // [2][NCOL][6]
+    static constexpr int INFO = PF + 12 * NCOL;   // int32 tables: colpart[NCOL], cycz[NCOL], laneOff[NCOL][32]
+    static constexpr int INFO_DOUBLES = (NCOL * 34 + 1) / 2;
+    static constexpr int TABLES = INFO + INFO_DOUBLES + ((INFO + INFO_DOUBLES) & 1);
+};
+
 template <int MC, bool TL, int TY, int TZ, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) sweepKernel(const SweepArgs A) {
     using L = SweepLayout<MC>;
+    using AL = AccLayout<TY, TZ>;
     constexpr int NPY = (TY + 1) / 2, NPZ = (TZ + 1) / 2, NP = NPY * NPZ, NB = (NP + NW - 1) / NW;
     constexpr int NCOL = TY * TZ;
-    constexpr int SEG = NCOL * 81;
+    constexpr int CS = AL::CS;
     constexpr int NT = NW * 32;
     static_assert((TY & 1) == 1 && (TZ & 1) == 1, "tile edge must be odd (2x2 element patches)");
 
     extern __shared__ double smem[];
-    double* seg0a = smem;            // dx=0 segment, ping
-    double* seg0b = seg0a + SEG;     // dx=0 segment, pong
-    double* segP = seg0b + SEG;      // lower plane, dx=+1
-    double* segM = segP + SEG;       // upper plane, dx=-1
-    double* pfA = segM + SEG;        // [NCOL][6] P,F of the lower plane
-    double* pfB = pfA + NCOL * 6;    // upper plane
-    double* tables = pfB + NCOL * 6; // [NW][4][PER_EL]
+    double* seg0a = smem + AL::OFF_0A;  // dx=0 segment, ping
+    double* seg0b = smem + AL::OFF_0B;  // dx=0 segment, pong
+    double* segP = smem + AL::OFF_P;    // lower plane, dx=+1
+    double* segM = smem + AL::OFF_M;    // upper plane, dx=-1
+    double* pfA = smem + AL::PF;        // [NCOL][6] P,F of the lower plane
+    double* pfB = pfA + NCOL * 6;       // upper plane
+    int* colPart = reinterpret_cast<int*>(smem + AL::INFO);
+    int* colCycz = colPart + NCOL;
+    int* laneOff = colCycz + NCOL;      // [NCOL][32]
+    double* tables = smem + AL::TABLES; // [NW][2][PER_EL]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NX = A.nX + 1, NY = A.nY + 1, NZ = A.nZ + 1;
@@ -92,7 +392,26 @@ __global__ void __launch_bounds__(NW * 32, 1) sweepKernel(const SweepArgs A) {
     const int xa = chunk * A.chunkLen, xb = min(xa + A.chunkLen, NX);
     const int exBegin = max(xa - 1, 0), exEnd = min(xb - 1, A.nX - 1);
 
-    for (int i = tid; i < 4 * SEG + 12 * NCOL; i += NT) smem[i] = 0.0;
+    for (int i = tid; i < AL::PF + 12 * NCOL; i += NT) smem[i] = 0.0;
+    // CSR row base of node (ix,iy,iz) in closed form: 9 * (sum of the degrees of all preceding nodes);
+    // deg = cx*cy*cz with c = 2 on a face, 3 inside (== plan->adjPtr, checked by the parity tests).
+    // base = 9 * (pre(ix)*totY*totZ + cx * colPart),  colPart = pre(iy)*totZ + cy*pre(iz).
+    auto pre = [](int i) { return i == 0 ? 0 : 3 * i - 1; };
+    const int totY = 3 * NY - 2, totZ = 3 * NZ - 2;
+    for (int t = tid; t < NCOL * 32; t += NT) {
+        const int col = t >> 5, e = t & 31;
+        const int ly = col / TZ, lz = col % TZ;
+        const int iy = y0 + ly, iz = z0 + lz;
+        const bool colValid = ly < ny && lz < nz;
+        const int cy = (iy > 0) + 1 + (iy < NY - 1), cz = (iz > 0) + 1 + (iz < NZ - 1);
+        if (e == 0) {
+            colPart[col] = colValid ? pre(iy) * totZ + cy * pre(iz) : 0;
+            colCycz[col] = colValid ? cy * cz : 0;
+        }
+        const int s9 = e / 3, j = e % 3, dy = s9 / 3 - 1, dz = s9 % 3 - 1;
+        const bool ok = colValid && e < 27 && iy + dy >= 0 && iy + dy < NY && iz + dz >= 0 && iz + dz < NZ;
+        laneOff[t] = ok ? 3 * ((dy + (iy > 0 ? 1 : 0)) * cz + dz + (iz > 0 ? 1 : 0)) + j : -1;
+    }
     __syncthreads();
 
     double* lo0 = seg0a;
@@ -101,40 +420,33 @@ __global__ void __launch_bounds__(NW * 32, 1) sweepKernel(const SweepArgs A) {
     double* pfHi = pfB;
     const int64_t cstride = (int64_t)A.nX * A.nY * A.nZ * 8;
     const double* __restrict__ uSrc = TL ? A.U : A.dU;
+    const int64_t totYZ = (int64_t)totY * totZ;
 
-    // CSR row base of node (ix,iy,iz) in closed form: 9 * (sum of the degrees of all preceding nodes);
-    // deg = cx*cy*cz with c = 2 on a face, 3 inside (== plan->adjPtr, checked by the parity tests)
-    auto pre = [](int i) { return i == 0 ? 0 : 3 * i - 1; };
-    const int64_t totY = 3 * NY - 2, totZ = 3 * NZ - 2;
-    // lane-fixed part of the flush mapping: lane e < 27 copies entry (s9 = e/3, j = e%3) of a 27-entry sub-row
-    const int fl_s9 = lane / 3, fl_j = lane % 3, fl_dy = fl_s9 / 3 - 1, fl_dz = fl_s9 % 3 - 1;
     // flush the finished segments (dx = -1, 0, +1; nullptr = not finished) of every owned node of plane ix, clear them
     auto flushPlane = [&](int ix, double* sM, double* s0, double* sP) {
         const int cx = (ix > 0) + 1 + (ix < NX - 1);
+        const int64_t xbase = (int64_t)pre(ix) * totYZ;
+        const int rx0 = ix > 0 ? 1 : 0;
         for (int col = warp; col < NCOL; col += NW) {
-            const int ly = col / TZ, lz = col % TZ;
-            if (ly >= ny || lz >= nz) continue;
-            const int iy = y0 + ly, iz = z0 + lz;
-            const int cy = (iy > 0) + 1 + (iy < NY - 1), cz = (iz > 0) + 1 + (iz < NZ - 1);
-            const int deg = cx * cy * cz;
-            const int64_t base = 9 * ((int64_t)pre(ix) * totY * totZ + (int64_t)cx * (pre(iy) * totZ + (int64_t)cy * pre(iz)));
-            const bool nbValid = lane < 27 && iy + fl_dy >= 0 && iy + fl_dy < NY && iz + fl_dz >= 0 && iz + fl_dz < NZ;
-            const int slotYZ = (fl_dy + (iy > 0 ? 1 : 0)) * cz + fl_dz + (iz > 0 ? 1 : 0);
+            const int cycz = colCycz[col];
+            if (cycz == 0) continue;
+            const int lo = laneOff[col * 32 + lane];
+            const int64_t base = 9 * (xbase + (int64_t)cx * colPart[col]);
+            const int64_t rowStride = 3 * cx * cycz;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 double* seg = d == 0 ? sM : (d == 1 ? s0 : sP);
                 if (seg == nullptr) continue;
                 const int dx = d - 1;
                 const bool dxValid = ix + dx >= 0 && ix + dx < NX;
-                const int rx = dx + (ix > 0 ? 1 : 0);
-                double* src = seg + col * 81 + lane;
-                double* dst = A.data + base + 3 * (rx * cy * cz + slotYZ) + fl_j;
                 if (lane < 27) {
+                    double* src = seg + col * CS + lane;
+                    double* dst = A.data + base + 3 * ((dx + rx0) * cycz) + lo;
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
                         const double v = src[i * 27];
                         src[i * 27] = 0.0;
-                        if (dxValid && nbValid) dst[(int64_t)i * 3 * deg] = v;
+                        if (dxValid && lo >= 0) dst[i * rowStride] = v;
                     }
                 }
             }
@@ -159,219 +471,84 @@ __global__ void __launch_bounds__(NW * 32, 1) sweepKernel(const SweepArgs A) {
         }
     };
 
+    double* wt = tables + (size_t)warp * 2 * L::PER_EL;
     for (int ex = exBegin; ex <= exEnd; ++ex) {
         const bool loOwned = ex >= xa, hiOwned = (ex + 1) < xb;
 #pragma unroll 1
         for (int bt = 0; bt < NB; ++bt) {
             const int p = bt * NW + warp;
             const int pyq = p / NPZ, pzq = p % NPZ;
-            double* wt = tables + (size_t)warp * 4 * L::PER_EL;
-            // ---------------- phase A: lane = (element k of the patch, Gauss point) ----------------
-            if (p < NP) {
-                const int k = lane >> 3, gp = lane & 7;
-                const int py = 2 * pyq + (k >> 1), pz = 2 * pzq + (k & 1);
-                const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
-                const bool valid = ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz;
-                if (valid) {
-                    double X[24], uu[24];
-#pragma unroll
-                    for (int a = 0; a < 8; ++a) {
-                        const int64_t n = ((int64_t)(ex + ndx(a)) * NY + (ey + ndy(a))) * NZ + (ez + ndz(a));
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            X[a * 3 + c] = __ldg(A.coords + 3 * n + c);
-                            uu[a * 3 + c] = __ldg(uSrc + 3 * n + c);
-                        }
-                    }
-                    const int64_t e = ((int64_t)ex * A.nY + ey) * A.nZ + ez;
-                    const int64_t off = e * 8 + gp;
-                    const bool writeState = loOwned && py >= 1 && pz >= 1;
-                    gaussPointL<L, 8, 8, MC, TL>(wt + k * L::PER_EL, X, uu, gp, A.mp, A.stateRef + off, A.stateTemp + off, cstride, writeState, A.failFlag);
-                }
-            }
-            __syncthreads();
-            // ---------------- phase B: 4 colour rounds, one element per warp per round -------------
 #pragma unroll 1
-            for (int k = 0; k < 4; ++k) {
-                const int py = 2 * pyq + (k >> 1), pz = 2 * pzq + (k & 1);
-                const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
-                const bool valid = p < NP && ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz;
-                if (valid) {
-                    const double* T = wt + k * L::PER_EL;
-                    const int r = lane >> 2, q = lane & 3;
-                    double g[2][3], K0[9], K1[9], Pr[3] = {0, 0, 0};
+            for (int pass = 0; pass < 2; ++pass) {
+                // ------------- phase A: lane = (element slot e2, Gauss point, node half) -------------
+                if (p < NP) {
+                    const int e2 = lane >> 4, gp = (lane >> 1) & 7, h = lane & 1;
+                    const int k = 2 * pass + e2;  // colour = position in the 2x2 patch
+                    const int py = 2 * pyq + (k >> 1), pz = 2 * pzq + (k & 1);
+                    const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
+                    const bool valid = ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz;
+                    if (valid) {
+                        double Xh[12], uh[12];
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
+                        for (int a = 0; a < 4; ++a) {
+                            // node a + 4h: dy = h, (dx,dz) of a
+                            const int64_t n = ((int64_t)(ex + ndx(a)) * NY + (ey + h)) * NZ + (ez + ndz(a));
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) g[ks][c] = T[L::OFF_G + (4 * ks + q) * L::GST + r * 3 + c];
-                    // residual row partial: (-w detJ S) v_r over this lane's two Gauss points
-                    if constexpr (MC == MC_LE) {
-                        double c[3][3][2];
-#pragma unroll
-                        for (int i = 0; i < 3; ++i)
-#pragma unroll
-                            for (int j = 0; j < 3; ++j) c[i][j][0] = c[i][j][1] = 0.0;
-#pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const double* co = T + L::OFF_CO + (4 * ks + q) * L::NCO;
-                            const double w = co[0];
-                            const double* S = co + 4;
-                            Pr[0] += S[0] * g[ks][0] + S[3] * g[ks][1] + S[4] * g[ks][2];
-                            Pr[1] += S[3] * g[ks][0] + S[1] * g[ks][1] + S[5] * g[ks][2];
-                            Pr[2] += S[4] * g[ks][0] + S[5] * g[ks][1] + S[2] * g[ks][2];
-                            if (A.wantK) {
-#pragma unroll
-                                for (int i = 0; i < 3; ++i) {
-                                    const double ai = w * g[ks][i];
-#pragma unroll
-                                    for (int j = 0; j < 3; ++j) dmma(c[i][j], ai, g[ks][j]);
-                                }
+                            for (int c = 0; c < 3; ++c) {
+                                Xh[a * 3 + c] = __ldg(A.coords + 3 * n + c);
+                                uh[a * 3 + c] = __ldg(uSrc + 3 * n + c);
                             }
                         }
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            double* Kt = t ? K1 : K0;
-                            const double tr = A.mp.G * (c[0][0][t] + c[1][1][t] + c[2][2][t]);
-#pragma unroll
-                            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                                for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = A.mp.lambda * c[i][j][t] + A.mp.G * c[j][i][t] + (i == j ? tr : 0.0);
-                        }
-                    } else if constexpr (MC == MC_VM) {
-                        double c1[3][3][2], c2[3][3][2];
-#pragma unroll
-                        for (int i = 0; i < 3; ++i)
-#pragma unroll
-                            for (int j = 0; j < 3; ++j) c1[i][j][0] = c1[i][j][1] = c2[i][j][0] = c2[i][j][1] = 0.0;
-#pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const double* co = T + L::OFF_CO + (4 * ks + q) * L::NCO;
-                            const double cl = co[0], cm = co[1], ca = co[2];
-                            const double* S = co + 4;
-                            const double* n = co + 10;
-                            Pr[0] += S[0] * g[ks][0] + S[3] * g[ks][1] + S[4] * g[ks][2];
-                            Pr[1] += S[3] * g[ks][0] + S[1] * g[ks][1] + S[5] * g[ks][2];
-                            Pr[2] += S[4] * g[ks][0] + S[5] * g[ks][1] + S[2] * g[ks][2];
-                            if (A.wantK) {
-                                double pv[3];
-                                pv[0] = n[0] * g[ks][0] + n[3] * g[ks][1] + n[4] * g[ks][2];
-                                pv[1] = n[3] * g[ks][0] + n[1] * g[ks][1] + n[5] * g[ks][2];
-                                pv[2] = n[4] * g[ks][0] + n[5] * g[ks][1] + n[2] * g[ks][2];
-#pragma unroll
-                                for (int i = 0; i < 3; ++i) {
-                                    const double li = cl * g[ks][i], mi = cm * g[ks][i], ri = ca * pv[i];
-#pragma unroll
-                                    for (int j = 0; j < 3; ++j) {
-                                        dmma(c1[i][j], li, g[ks][j]);
-                                        dmma(c1[i][j], ri, pv[j]);
-                                        dmma(c2[i][j], mi, g[ks][j]);
-                                    }
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            double* Kt = t ? K1 : K0;
-                            const double tr = c2[0][0][t] + c2[1][1][t] + c2[2][2][t];
-#pragma unroll
-                            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                                for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = c1[i][j][t] + c2[j][i][t] + (i == j ? tr : 0.0);
-                        }
-                    } else {
-                        double c1[3][3][2], c2[3][3][2], d0[3][2];
-#pragma unroll
-                        for (int i = 0; i < 3; ++i) {
-                            d0[i][0] = d0[i][1] = 0.0;
-#pragma unroll
-                            for (int j = 0; j < 3; ++j) c1[i][j][0] = c1[i][j][1] = c2[i][j][0] = c2[i][j][1] = 0.0;
-                        }
-                        const bool wb = (A.mp.kind == EWB_MAT_NEOHOOKE_WB);
-#pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const double* co = T + L::OFF_CO + (4 * ks + q) * L::NCO;
-                            const double k0 = co[0], k1 = co[1], k2 = co[2], k4 = co[3];
-                            const double* S = co + 4;
-                            const double* F = co + 10;
-                            const double* iF = co + 19;
-                            double nv[3];
-#pragma unroll
-                            for (int m = 0; m < 3; ++m) nv[m] = g[ks][0] * iF[m] + g[ks][1] * iF[3 + m] + g[ks][2] * iF[6 + m];
-                            Pr[0] += S[0] * nv[0] + S[3] * nv[1] + S[4] * nv[2];
-                            Pr[1] += S[3] * nv[0] + S[1] * nv[1] + S[5] * nv[2];
-                            Pr[2] += S[4] * nv[0] + S[5] * nv[1] + S[2] * nv[2];
-                            if (A.wantK) {
-#pragma unroll
-                                for (int i = 0; i < 3; ++i) {
-                                    const double a1 = k1 * nv[i], a2 = k2 * nv[i];
-                                    dmma(d0[i], k0 * g[ks][i], g[ks][i]);
-#pragma unroll
-                                    for (int j = 0; j < 3; ++j) {
-                                        dmma(c1[i][j], a1, nv[j]);
-                                        dmma(c2[i][j], a2, nv[j]);
-                                    }
-                                }
-                                if (wb) {  // W_b: + c4 (f_a n_b^T + n_a f_b^T), f = F g
-                                    double fv[3];
-#pragma unroll
-                                    for (int i = 0; i < 3; ++i) fv[i] = F[i * 3] * g[ks][0] + F[i * 3 + 1] * g[ks][1] + F[i * 3 + 2] * g[ks][2];
-#pragma unroll
-                                    for (int i = 0; i < 3; ++i)
-#pragma unroll
-                                        for (int j = 0; j < 3; ++j) {
-                                            dmma(c1[i][j], k4 * fv[i], nv[j]);
-                                            dmma(c1[i][j], k4 * nv[i], fv[j]);
-                                        }
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            double* Kt = t ? K1 : K0;
-                            const double tr = d0[0][t] + d0[1][t] + d0[2][t];
-#pragma unroll
-                            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                                for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = c1[i][j][t] + c2[j][i][t] + (i == j ? tr : 0.0);
-                        }
-                    }
-                    // reduce the residual row over the 4 lanes (Gauss-point pairs) of node r
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        Pr[i] += __shfl_xor_sync(0xffffffffu, Pr[i], 1);
-                        Pr[i] += __shfl_xor_sync(0xffffffffu, Pr[i], 2);
-                    }
-                    // ---- accumulate into the owned rows ----
-                    const int a = r;
-                    const int ly = py - 1 + ndy(a), lz = pz - 1 + ndz(a);
-                    const bool owned = ly >= 0 && ly < ny && lz >= 0 && lz < nz && (ndx(a) ? hiOwned : loOwned);
-                    if (owned) {
-                        const int col = ly * TZ + lz;
-                        if (q == 0) {
-                            double* pf = (ndx(a) ? pfHi : pfLo) + col * 6;
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                pf[i] += Pr[i];
-                                pf[3 + i] += fabs(Pr[i]);
-                            }
-                        }
-                        if (A.wantK) {
-#pragma unroll
-                            for (int t = 0; t < 2; ++t) {
-                                const int b = 2 * q + t;
-                                const int rx = ndx(b) - ndx(a), ry = ndy(b) - ndy(a), rz = ndz(b) - ndz(a);
-                                double* seg = ndx(a) ? (rx == 0 ? hi0 : segM) : (rx == 0 ? lo0 : segP);
-                                double* dst = seg + col * 81 + ((ry + 1) * 3 + rz + 1) * 3;
-                                const double* Kt = t ? K1 : K0;
-#pragma unroll
-                                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                                    for (int j = 0; j < 3; ++j) dst[i * 27 + j] += Kt[i * 3 + j];
-                            }
-                        }
+                        const int64_t e = ((int64_t)ex * A.nY + ey) * A.nZ + ez;
+                        const int64_t off = e * 8 + gp;
+                        const bool writeState = loOwned && py >= 1 && pz >= 1;
+                        gaussPointHalf<L, MC, TL>(wt + e2 * L::PER_EL, Xh, uh, gp, h, 0xffffu << (16 * e2), A.mp, A.stateRef + off,
+                                                  A.stateTemp + off, cstride, writeState, A.failFlag);
                     }
                 }
                 __syncthreads();
+                // ------------- phase B: 2 colour rounds, one element per warp per round -------------
+#pragma unroll 1
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int k = 2 * pass + rr;
+                    const int py = 2 * pyq + (k >> 1), pz = 2 * pzq + (k & 1);
+                    const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
+                    const bool valid = p < NP && ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz;
+                    if (valid) {
+                        double K0[9], K1[9], Pr[3];
+                        elementBlocks<MC>(wt + rr * L::PER_EL, lane, A.mp, A.wantK != 0, K0, K1, Pr);
+                        // ---- accumulate into the owned rows ----
+                        const int a = lane >> 2, q = lane & 3;
+                        const int ly = py - 1 + ndy(a), lz = pz - 1 + ndz(a);
+                        const bool owned = ly >= 0 && ly < ny && lz >= 0 && lz < nz && (ndx(a) ? hiOwned : loOwned);
+                        if (owned) {
+                            const int col = ly * TZ + lz;
+                            if (q == 0) {
+                                double* pf = (ndx(a) ? pfHi : pfLo) + col * 6;
+#pragma unroll
+                                for (int i = 0; i < 3; ++i) {
+                                    pf[i] += Pr[i];
+                                    pf[3 + i] += fabs(Pr[i]);
+                                }
+                            }
+                            if (A.wantK) {
+#pragma unroll
+                                for (int t = 0; t < 2; ++t) {
+                                    const int b = 2 * q + t;
+                                    const int rx = ndx(b) - ndx(a), ry = ndy(b) - ndy(a), rz = ndz(b) - ndz(a);
+                                    double* seg = ndx(a) ? (rx == 0 ? hi0 : segM) : (rx == 0 ? lo0 : segP);
+                                    double* dst = seg + col * CS + ((ry + 1) * 3 + rz + 1) * 3;
+                                    const double* Kt = t ? K1 : K0;
+#pragma unroll
+                                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                                        for (int j = 0; j < 3; ++j) dst[i * 27 + j] += Kt[i * 3 + j];
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
             }
         }
         // ---------------- flush the finished segments, rotate ----------------
@@ -395,6 +572,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sweepKernel(const SweepArgs A) {
 struct SweepPlan {
     int64_t nX = 0, nY = 0, nZ = 0;
     const int64_t* adjPtr = nullptr;
+    int nSM = 148;
 
     int build(int64_t nx, int64_t ny, int64_t nz) {
         nX = nx; nY = ny; nZ = nz;
@@ -409,17 +587,24 @@ struct SweepPlan {
         a.nX = (int)nX; a.nY = (int)nY; a.nZ = (int)nZ;
         a.tilesY = (int)((nY + 1 + TY - 1) / TY);
         a.tilesZ = (int)((nZ + 1 + TZ - 1) / TZ);
-        // chunks along x: enough CTAs for >= ~6 waves of 148 SMs, at least ~12 planes per chunk
+        // chunks along x: minimise (number of CTA rounds on nSM SMs) x (planes per chunk incl. the halo plane)
         const int64_t tiles = (int64_t)a.tilesY * a.tilesZ;
-        int nChunks = (int)std::max<int64_t>(1, std::min<int64_t>((nX + 1) / 12, (148 * 6 + tiles - 1) / tiles));
-        a.chunkLen = (int)((nX + 1 + nChunks - 1) / nChunks);
+        int best = 1;
+        double bestCost = 1e300;
+        for (int c = 1; c <= 64 && (nX + 1) / c >= 6; ++c) {
+            const int64_t len = (nX + 1 + c - 1) / c, nc = (nX + 1 + len - 1) / len;
+            const double rounds = (double)((tiles * nc + nSM - 1) / nSM);
+            const double cost = rounds * (double)(len + 1);
+            if (cost < bestCost) { bestCost = cost; best = c; }
+        }
+        a.chunkLen = (int)((nX + 1 + best - 1) / best);
         a.nChunks = (int)((nX + 1 + a.chunkLen - 1) / a.chunkLen);
         a.coords = b->coords; a.U = b->U; a.dU = b->dU; a.stateRef = b->state_ref; a.stateTemp = b->state_temp;
         a.data = b->csr_data; a.P = b->P; a.F = b->F; a.adjPtr = adjPtr; a.mp = mp; a.failFlag = failFlag;
         a.wantK = (flags & EWB_FLAG_NO_STIFFNESS) ? 0 : 1;
         a.accumulatePF = (flags & EWB_FLAG_ACCUMULATE_PF) ? 1 : 0;
         auto kern = sweepKernel<MC, TL, TY, TZ, NW>;
-        const size_t smem = ((size_t)4 * TY * TZ * 81 + 12 * TY * TZ + (size_t)NW * 4 * Lay::PER_EL) * sizeof(double);
+        const size_t smem = ((size_t)AccLayout<TY, TZ>::TABLES + (size_t)NW * 2 * Lay::PER_EL) * sizeof(double);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EWB_ERR_CUDA;
         const int64_t grid = tiles * a.nChunks;
         kern<<<(unsigned)grid, NW * 32, smem, st>>>(a);
@@ -428,9 +613,9 @@ struct SweepPlan {
 
     int launch(int elType, int mc, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st, int* launches) {
         int rc = EWB_ERR_UNSUPPORTED;
-        if (elType == EWB_C3D8 && mc == MC_LE) rc = launchT<MC_LE, false, 7, 7, 8>(mp, b, failFlag, flags, st);
-        else if (elType == EWB_C3D8 && mc == MC_VM) rc = launchT<MC_VM, false, 7, 7, 8>(mp, b, failFlag, flags, st);
-        else if (elType == EWB_C3D8TL && mc == MC_NH) rc = launchT<MC_NH, true, 7, 7, 4>(mp, b, failFlag, flags, st);
+        if (elType == EWB_C3D8 && mc == MC_LE) rc = launchT<MC_LE, false, 7, 7, 16>(mp, b, failFlag, flags, st);
+        else if (elType == EWB_C3D8 && mc == MC_VM) rc = launchT<MC_VM, false, 7, 7, 16>(mp, b, failFlag, flags, st);
+        else if (elType == EWB_C3D8TL && mc == MC_NH) rc = launchT<MC_NH, true, 7, 7, 8>(mp, b, failFlag, flags, st);
         if (rc == EWB_OK) *launches = 1;
         return rc;
     }
