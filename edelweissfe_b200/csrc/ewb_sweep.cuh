@@ -61,14 +61,18 @@ __device__ __forceinline__ int ndx(int a) { return (a >> 1) & 1; }
 __device__ __forceinline__ int ndy(int a) { return (a >> 2) & 1; }
 __device__ __forceinline__ int ndz(int a) { return (a ^ (a >> 1)) & 1; }
 
+// mma row/column r  <->  local node ROWPERM[r] = {0,1,3,2,5,4,6,7}[r]  (fewest bank conflicts, see AccLayout)
+__device__ __forceinline__ int rowNode(int r) { return (0x76452310u >> (4 * r)) & 7; }
+
 // Phase B for ONE element by one warp: lane (r = lane>>2, q = lane&3) ends with the 3x3 stiffness blocks
-// K0 = K[node r][node 2q], K1 = K[node r][node 2q+1] and (all 4 lanes of r) the residual row Pr of node r.
+// K0 = K[node a][node b0], K1 = K[node a][node b1] (a = rowNode(lane>>2), b_t = rowNode(2q+t)) and (all 4 lanes
+// of a row) the residual row Pr of node a.
 // T: the element's shared-memory tables written by phase A.
 template <int MC>
 __device__ __forceinline__ void elementBlocks(const double* T, int lane, const MatParams& mp, bool wantK, double (&K0)[9], double (&K1)[9],
                                               double (&Pr)[3]) {
     using L = SweepLayout<MC>;
-    const int r = lane >> 2, q = lane & 3;
+    const int r = rowNode(lane >> 2), q = lane & 3;
     double g[2][3];
     Pr[0] = Pr[1] = Pr[2] = 0.0;
 #pragma unroll
@@ -344,28 +348,54 @@ __device__ __forceinline__ void gaussPointHalf(double* sm, const double (&Xh)[12
     }
 }
 
-// Accumulator geometry (doubles): per node column CS, 4 segments, offsets chosen for few bank conflicts.
+// Accumulator geometry (doubles).  Per node column 81 doubles per segment, laid out [i][s9][j] so that a
+// CSR sub-row (27 values) is contiguous.  The four segment bases sit at residues 0,7,8,15 (mod 16 doubles)
+// and the mma rows are permuted (ROWPERM) — together the cheapest bank pattern found by exhaustive search
+// for the accumulation stores (tools/bank_search.py): 1.5 wavefronts per half-warp instead of 3.0.
+__host__ __device__ constexpr int alignRes(int x, int r) { return x + ((r - x % 16) + 16) % 16; }
 template <int TY, int TZ>
 struct AccLayout {
     static constexpr int NCOL = TY * TZ;
-    static constexpr int CS = 81;                 // [i][s9][j]: row i of a segment = 27 contiguous doubles
-    static constexpr int SEG = NCOL * CS + 7;     // 49*81+7 == 8 (mod 16)
-    static constexpr int OFF_0A = 0, OFF_0B = SEG, OFF_P = 2 * SEG, OFF_M = 3 * SEG;
-    static constexpr int PF = 4 * SEG;            // [2][NCOL][6]
-    static constexpr int INFO = PF + 12 * NCOL;   // int32 tables: colpart[NCOL], cycz[NCOL], laneOff[NCOL][32]
-    static constexpr int INFO_DOUBLES = (NCOL * 34 + 1) / 2;
-    static constexpr int TABLES = INFO + INFO_DOUBLES + ((INFO + INFO_DOUBLES) & 1);
+    static constexpr int CS = 81;
+    static constexpr int SEGSZ = NCOL * CS;
+    static constexpr int OFF_0A = 0;
+    static constexpr int OFF_0B = alignRes(OFF_0A + SEGSZ, 7);
+    static constexpr int OFF_P = alignRes(OFF_0B + SEGSZ, 8);
+    static constexpr int OFF_M = alignRes(OFF_P + SEGSZ, 15);
+    static constexpr int ACC_END = OFF_M + SEGSZ;
+    static constexpr int PF = ACC_END;               // [2][NCOL][6]
+    static constexpr int INFO = PF + 12 * NCOL;      // int32: colPart[NCOL], colCycz[NCOL], laneOff[NCOL][32], done[32], flushed[32]
+    static constexpr int INFO_INTS = NCOL * 34 + 64;
+    static constexpr int TABLES = alignRes(INFO + (INFO_INTS + 1) / 2, 0);
 };
 
-template <int MC, bool TL, int TY, int TZ, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) sweepKernel(const SweepArgs A) {
+// Warp-level wait until flag[dep] >= target for up to 9 dependencies (lane i polls dependency i).
+// Bounded: a logic error sets bit 2 of the status word instead of hanging the GPU.
+__device__ __forceinline__ void waitFlags(const volatile int* flag, int dep, bool has, int target, int* failFlag) {
+    int spins = 0;
+    while (true) {
+        const bool ok = !has || flag[dep] >= target;
+        if (__all_sync(0xffffffffu, ok)) break;
+        if (++spins > (1 << 22)) {
+            atomicOr(failFlag, 4);
+            break;
+        }
+        __nanosleep(20);
+    }
+    __threadfence_block();
+}
+
+// One warp per 2x2 element patch; NW == number of patches of the tile.
+template <int MC, bool TL, int TY, int TZ>
+__global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweepKernel(const SweepArgs A) {
     using L = SweepLayout<MC>;
     using AL = AccLayout<TY, TZ>;
-    constexpr int NPY = (TY + 1) / 2, NPZ = (TZ + 1) / 2, NP = NPY * NPZ, NB = (NP + NW - 1) / NW;
+    constexpr int NPY = (TY + 1) / 2, NPZ = (TZ + 1) / 2, NW = NPY * NPZ;
     constexpr int NCOL = TY * TZ;
     constexpr int CS = AL::CS;
     constexpr int NT = NW * 32;
     static_assert((TY & 1) == 1 && (TZ & 1) == 1, "tile edge must be odd (2x2 element patches)");
+    static_assert(NW <= 32, "at most 32 patches per tile");
 
     extern __shared__ double smem[];
     double* seg0a = smem + AL::OFF_0A;  // dx=0 segment, ping
@@ -377,6 +407,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sweepKernel(const SweepArgs A) {
     int* colPart = reinterpret_cast<int*>(smem + AL::INFO);
     int* colCycz = colPart + NCOL;
     int* laneOff = colCycz + NCOL;      // [NCOL][32]
+    volatile int* doneCnt = laneOff + NCOL * 32;  // [32] rounds completed per patch
+    volatile int* flushedCnt = doneCnt + 32;      // [32] plane steps flushed per patch
     double* tables = smem + AL::TABLES; // [NW][2][PER_EL]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -392,7 +424,8 @@ __global__ void __launch_bounds__(NW * 32, 1) sweepKernel(const SweepArgs A) {
     const int xa = chunk * A.chunkLen, xb = min(xa + A.chunkLen, NX);
     const int exBegin = max(xa - 1, 0), exEnd = min(xb - 1, A.nX - 1);
 
-    for (int i = tid; i < AL::PF + 12 * NCOL; i += NT) smem[i] = 0.0;
+    for (int i = tid; i < AL::INFO; i += NT) smem[i] = 0.0;
+    if (tid < 64) doneCnt[tid] = 0;
     // CSR row base of node (ix,iy,iz) in closed form: 9 * (sum of the degrees of all preceding nodes);
     // deg = cx*cy*cz with c = 2 on a face, 3 inside (== plan->adjPtr, checked by the parity tests).
     // base = 9 * (pre(ix)*totY*totZ + cx * colPart),  colPart = pre(iy)*totZ + cy*pre(iz).
@@ -412,7 +445,7 @@ __global__ void __launch_bounds__(NW * 32, 1) sweepKernel(const SweepArgs A) {
         const bool ok = colValid && e < 27 && iy + dy >= 0 && iy + dy < NY && iz + dz >= 0 && iz + dz < NZ;
         laneOff[t] = ok ? 3 * ((dy + (iy > 0 ? 1 : 0)) * cz + dz + (iz > 0 ? 1 : 0)) + j : -1;
     }
-    __syncthreads();
+    __syncthreads();  // the only CTA-wide barrier: from here on the warps are ordered by dataflow flags
 
     double* lo0 = seg0a;
     double* hi0 = seg0b;
@@ -422,150 +455,174 @@ __global__ void __launch_bounds__(NW * 32, 1) sweepKernel(const SweepArgs A) {
     const double* __restrict__ uSrc = TL ? A.U : A.dU;
     const int64_t totYZ = (int64_t)totY * totZ;
 
-    // flush the finished segments (dx = -1, 0, +1; nullptr = not finished) of every owned node of plane ix, clear them
-    auto flushPlane = [&](int ix, double* sM, double* s0, double* sP) {
+    // this warp's patch and its dependencies
+    const int p = warp, pyq = p / NPZ, pzq = p % NPZ;
+    // (1) emission of round R waits for the 8 neighbouring patches to have finished round R-1
+    int depN = 0; bool hasN = false;
+    if (lane < 9) {
+        const int qy = pyq + lane / 3 - 1, qz = pzq + lane % 3 - 1;
+        hasN = lane != 4 && qy >= 0 && qy < NPY && qz >= 0 && qz < NPZ;
+        depN = hasN ? qy * NPZ + qz : 0;
+    }
+    // (2) the first emission of a plane step waits for the owners of the columns it touches to have flushed the previous step
+    int depF = 0; bool hasF = false;
+    if (lane < 4) {
+        const int qy = pyq - (lane >> 1), qz = pzq - (lane & 1);
+        hasF = qy >= 0 && qz >= 0;
+        depF = hasF ? qy * NPZ + qz : 0;
+    }
+    // (3) the flush of this warp's columns (2pyq+{0,1}, 2pzq+{0,1}) waits for the patches that touch them
+    int depD = 0; bool hasD = false;
+    if (lane < 4) {
+        const int qy = pyq + (lane >> 1), qz = pzq + (lane & 1);
+        hasD = qy < NPY && qz < NPZ;
+        depD = hasD ? qy * NPZ + qz : 0;
+    }
+
+    // flush the finished segments (nullptr = not finished) of this warp's owned nodes of plane ix, clear them
+    auto flushPlane = [&](int ix, double* sM, double* s0, double* sP, double* pf) {
         const int cx = (ix > 0) + 1 + (ix < NX - 1);
         const int64_t xbase = (int64_t)pre(ix) * totYZ;
         const int rx0 = ix > 0 ? 1 : 0;
-        for (int col = warp; col < NCOL; col += NW) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int ly = 2 * pyq + (cc >> 1), lz = 2 * pzq + (cc & 1);
+            if (ly >= TY || lz >= TZ) continue;
+            const int col = ly * TZ + lz;
             const int cycz = colCycz[col];
             if (cycz == 0) continue;
             const int lo = laneOff[col * 32 + lane];
             const int64_t base = 9 * (xbase + (int64_t)cx * colPart[col]);
             const int64_t rowStride = 3 * cx * cycz;
+            if (A.wantK) {
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                double* seg = d == 0 ? sM : (d == 1 ? s0 : sP);
-                if (seg == nullptr) continue;
-                const int dx = d - 1;
-                const bool dxValid = ix + dx >= 0 && ix + dx < NX;
-                if (lane < 27) {
-                    double* src = seg + col * CS + lane;
-                    double* dst = A.data + base + 3 * ((dx + rx0) * cycz) + lo;
+                for (int d = 0; d < 3; ++d) {
+                    double* seg = d == 0 ? sM : (d == 1 ? s0 : sP);
+                    if (seg == nullptr) continue;
+                    const int dx = d - 1;
+                    const bool dxValid = ix + dx >= 0 && ix + dx < NX;
+                    if (lane < 27) {
+                        double* src = seg + col * CS + lane;
+                        double* dst = A.data + base + 3 * ((dx + rx0) * cycz) + lo;
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const double v = src[i * 27];
-                        src[i * 27] = 0.0;
-                        if (dxValid && lo >= 0) dst[i * rowStride] = v;
+                        for (int i = 0; i < 3; ++i) {
+                            const double v = src[i * 27];
+                            src[i * 27] = 0.0;
+                            if (dxValid && lo >= 0) dst[i * rowStride] = v;
+                        }
                     }
                 }
             }
-        }
-    };
-    auto flushPF = [&](double* pf, int ix) {
-        for (int t = tid; t < NCOL * 3; t += NT) {
-            const int col = t / 3, i = t % 3;
-            const int ly = col / TZ, lz = col % TZ;
-            const double p = pf[col * 6 + i], f = pf[col * 6 + 3 + i];
-            pf[col * 6 + i] = 0.0;
-            pf[col * 6 + 3 + i] = 0.0;
-            if (ly >= ny || lz >= nz) continue;
-            const int64_t dof = 3 * ((((int64_t)ix * NY + (y0 + ly)) * NZ) + (z0 + lz)) + i;
-            if (A.accumulatePF) {
-                A.P[dof] += p;
-                A.F[dof] += f;
-            } else {
-                A.P[dof] = p;
-                A.F[dof] = f;
+            if (pf != nullptr && lane < 3) {
+                const double pv = pf[col * 6 + lane], fv = pf[col * 6 + 3 + lane];
+                pf[col * 6 + lane] = 0.0;
+                pf[col * 6 + 3 + lane] = 0.0;
+                const int64_t dof = 3 * ((((int64_t)ix * NY + (y0 + ly)) * NZ) + (z0 + lz)) + lane;
+                if (A.accumulatePF) {
+                    A.P[dof] += pv;
+                    A.F[dof] += fv;
+                } else {
+                    A.P[dof] = pv;
+                    A.F[dof] = fv;
+                }
             }
         }
     };
 
     double* wt = tables + (size_t)warp * 2 * L::PER_EL;
-    for (int ex = exBegin; ex <= exEnd; ++ex) {
+    int step = 0;
+    for (int ex = exBegin; ex <= exEnd; ++ex, ++step) {
         const bool loOwned = ex >= xa, hiOwned = (ex + 1) < xb;
 #pragma unroll 1
-        for (int bt = 0; bt < NB; ++bt) {
-            const int p = bt * NW + warp;
-            const int pyq = p / NPZ, pzq = p % NPZ;
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                // ------------- phase A: lane = (element slot e2, Gauss point, node half) -------------
-                if (p < NP) {
-                    const int e2 = lane >> 4, gp = (lane >> 1) & 7, h = lane & 1;
-                    const int k = 2 * pass + e2;  // colour = position in the 2x2 patch
-                    const int py = 2 * pyq + (k >> 1), pz = 2 * pzq + (k & 1);
-                    const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
-                    const bool valid = ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz;
-                    if (valid) {
-                        double Xh[12], uh[12];
+        for (int pass = 0; pass < 2; ++pass) {
+            // ------------- phase A: lane = (element slot e2, Gauss point, node half) -------------
+            {
+                const int e2 = lane >> 4, gp = (lane >> 1) & 7, h = lane & 1;
+                const int k = 2 * pass + e2;  // colour = position in the 2x2 patch
+                const int py = 2 * pyq + (k >> 1), pz = 2 * pzq + (k & 1);
+                const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
+                const bool valid = ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz;
+                if (valid) {
+                    double Xh[12], uh[12];
 #pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            // node a + 4h: dy = h, (dx,dz) of a
-                            const int64_t n = ((int64_t)(ex + ndx(a)) * NY + (ey + h)) * NZ + (ez + ndz(a));
+                    for (int a = 0; a < 4; ++a) {
+                        // node a + 4h: dy = h, (dx,dz) of a
+                        const int64_t n = ((int64_t)(ex + ndx(a)) * NY + (ey + h)) * NZ + (ez + ndz(a));
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                Xh[a * 3 + c] = __ldg(A.coords + 3 * n + c);
-                                uh[a * 3 + c] = __ldg(uSrc + 3 * n + c);
-                            }
-                        }
-                        const int64_t e = ((int64_t)ex * A.nY + ey) * A.nZ + ez;
-                        const int64_t off = e * 8 + gp;
-                        const bool writeState = loOwned && py >= 1 && pz >= 1;
-                        gaussPointHalf<L, MC, TL>(wt + e2 * L::PER_EL, Xh, uh, gp, h, 0xffffu << (16 * e2), A.mp, A.stateRef + off,
-                                                  A.stateTemp + off, cstride, writeState, A.failFlag);
-                    }
-                }
-                __syncthreads();
-                // ------------- phase B: 2 colour rounds, one element per warp per round -------------
-#pragma unroll 1
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int k = 2 * pass + rr;
-                    const int py = 2 * pyq + (k >> 1), pz = 2 * pzq + (k & 1);
-                    const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
-                    const bool valid = p < NP && ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz;
-                    if (valid) {
-                        double K0[9], K1[9], Pr[3];
-                        elementBlocks<MC>(wt + rr * L::PER_EL, lane, A.mp, A.wantK != 0, K0, K1, Pr);
-                        // ---- accumulate into the owned rows ----
-                        const int a = lane >> 2, q = lane & 3;
-                        const int ly = py - 1 + ndy(a), lz = pz - 1 + ndz(a);
-                        const bool owned = ly >= 0 && ly < ny && lz >= 0 && lz < nz && (ndx(a) ? hiOwned : loOwned);
-                        if (owned) {
-                            const int col = ly * TZ + lz;
-                            if (q == 0) {
-                                double* pf = (ndx(a) ? pfHi : pfLo) + col * 6;
-#pragma unroll
-                                for (int i = 0; i < 3; ++i) {
-                                    pf[i] += Pr[i];
-                                    pf[3 + i] += fabs(Pr[i]);
-                                }
-                            }
-                            if (A.wantK) {
-#pragma unroll
-                                for (int t = 0; t < 2; ++t) {
-                                    const int b = 2 * q + t;
-                                    const int rx = ndx(b) - ndx(a), ry = ndy(b) - ndy(a), rz = ndz(b) - ndz(a);
-                                    double* seg = ndx(a) ? (rx == 0 ? hi0 : segM) : (rx == 0 ? lo0 : segP);
-                                    double* dst = seg + col * CS + ((ry + 1) * 3 + rz + 1) * 3;
-                                    const double* Kt = t ? K1 : K0;
-#pragma unroll
-                                    for (int i = 0; i < 3; ++i)
-#pragma unroll
-                                        for (int j = 0; j < 3; ++j) dst[i * 27 + j] += Kt[i * 3 + j];
-                                }
-                            }
+                        for (int c = 0; c < 3; ++c) {
+                            Xh[a * 3 + c] = __ldg(A.coords + 3 * n + c);
+                            uh[a * 3 + c] = __ldg(uSrc + 3 * n + c);
                         }
                     }
-                    __syncthreads();
+                    const int64_t e = ((int64_t)ex * A.nY + ey) * A.nZ + ez;
+                    const int64_t off = e * 8 + gp;
+                    const bool writeState = loOwned && py >= 1 && pz >= 1;
+                    gaussPointHalf<L, MC, TL>(wt + e2 * L::PER_EL, Xh, uh, gp, h, 0xffffu << (16 * e2), A.mp, A.stateRef + off, A.stateTemp + off,
+                                              cstride, writeState, A.failFlag);
                 }
             }
+            __syncwarp();
+            // ------------- phase B: 2 colour rounds, one element per round -------------
+#pragma unroll 1
+            for (int rr = 0; rr < 2; ++rr) {
+                const int k = 2 * pass + rr;
+                const int R = 4 * step + k;
+                const int py = 2 * pyq + (k >> 1), pz = 2 * pzq + (k & 1);
+                const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
+                const bool valid = ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz;
+                double K0[9], K1[9], Pr[3];
+                if (valid) elementBlocks<MC>(wt + rr * L::PER_EL, lane, A.mp, A.wantK != 0, K0, K1, Pr);
+                // ---- ordering: same-colour elements of different patches never share a node ----
+                if (k == 0) waitFlags(flushedCnt, depF, hasF, step, A.failFlag);
+                waitFlags(doneCnt, depN, hasN, R, A.failFlag);
+                if (valid) {
+                    // ---- accumulate into the owned rows ----
+                    const int a = rowNode(lane >> 2), q = lane & 3;
+                    const int ly = py - 1 + ndy(a), lz = pz - 1 + ndz(a);
+                    const bool owned = ly >= 0 && ly < ny && lz >= 0 && lz < nz && (ndx(a) ? hiOwned : loOwned);
+                    if (owned) {
+                        const int col = ly * TZ + lz;
+                        if (q == 0) {
+                            double* pf = (ndx(a) ? pfHi : pfLo) + col * 6;
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) {
+                                pf[i] += Pr[i];
+                                pf[3 + i] += fabs(Pr[i]);
+                            }
+                        }
+                        if (A.wantK) {
+#pragma unroll
+                            for (int t = 0; t < 2; ++t) {
+                                const int b = rowNode(2 * q + t);
+                                const int rx = ndx(b) - ndx(a), ry = ndy(b) - ndy(a), rz = ndz(b) - ndz(a);
+                                double* seg = ndx(a) ? (rx == 0 ? hi0 : segM) : (rx == 0 ? lo0 : segP);
+                                double* dst = seg + col * CS + ((ry + 1) * 3 + rz + 1) * 3;
+                                const double* Kt = t ? K1 : K0;
+#pragma unroll
+                                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                                    for (int j = 0; j < 3; ++j) dst[i * 27 + j] += Kt[i * 3 + j];
+                            }
+                        }
+                    }
+                }
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) doneCnt[p] = R + 1;
+            }
         }
-        // ---------------- flush the finished segments, rotate ----------------
-        if (A.wantK) {
-            if (loOwned) flushPlane(ex, nullptr, lo0, segP);
-            if (hiOwned) flushPlane(ex + 1, segM, nullptr, nullptr);
-        }
-        if (loOwned) flushPF(pfLo, ex);
-        __syncthreads();
+        // ---------------- flush this warp's finished columns, rotate ----------------
+        waitFlags(doneCnt, depD, hasD, 4 * (step + 1), A.failFlag);
+        if (loOwned) flushPlane(ex, nullptr, lo0, segP, pfLo);
+        if (hiOwned) flushPlane(ex + 1, segM, nullptr, nullptr, nullptr);
+        if (ex == exEnd && xb == NX) flushPlane(NX - 1, nullptr, hi0, nullptr, pfHi);  // last node plane: nothing above it
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) flushedCnt[p] = step + 1;
         {
             double* t0 = lo0; lo0 = hi0; hi0 = t0;
             double* t1 = pfLo; pfLo = pfHi; pfHi = t1;
         }
-    }
-    if (xb == NX && exEnd + 1 == NX - 1) {  // the last node plane has no element plane above it
-        if (A.wantK) flushPlane(NX - 1, nullptr, lo0, nullptr);
-        flushPF(pfLo, NX - 1);
     }
 }
 
@@ -580,7 +637,7 @@ struct SweepPlan {
     }
     void release() {}
 
-    template <int MC, bool TL, int TY, int TZ, int NW>
+    template <int MC, bool TL, int TY, int TZ>
     int launchT(const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st) {
         using Lay = SweepLayout<MC>;
         SweepArgs a;
@@ -603,7 +660,8 @@ struct SweepPlan {
         a.data = b->csr_data; a.P = b->P; a.F = b->F; a.adjPtr = adjPtr; a.mp = mp; a.failFlag = failFlag;
         a.wantK = (flags & EWB_FLAG_NO_STIFFNESS) ? 0 : 1;
         a.accumulatePF = (flags & EWB_FLAG_ACCUMULATE_PF) ? 1 : 0;
-        auto kern = sweepKernel<MC, TL, TY, TZ, NW>;
+        constexpr int NW = ((TY + 1) / 2) * ((TZ + 1) / 2);
+        auto kern = sweepKernel<MC, TL, TY, TZ>;
         const size_t smem = ((size_t)AccLayout<TY, TZ>::TABLES + (size_t)NW * 2 * Lay::PER_EL) * sizeof(double);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EWB_ERR_CUDA;
         const int64_t grid = tiles * a.nChunks;
@@ -613,9 +671,9 @@ struct SweepPlan {
 
     int launch(int elType, int mc, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st, int* launches) {
         int rc = EWB_ERR_UNSUPPORTED;
-        if (elType == EWB_C3D8 && mc == MC_LE) rc = launchT<MC_LE, false, 7, 7, 16>(mp, b, failFlag, flags, st);
-        else if (elType == EWB_C3D8 && mc == MC_VM) rc = launchT<MC_VM, false, 7, 7, 16>(mp, b, failFlag, flags, st);
-        else if (elType == EWB_C3D8TL && mc == MC_NH) rc = launchT<MC_NH, true, 7, 7, 8>(mp, b, failFlag, flags, st);
+        if (elType == EWB_C3D8 && mc == MC_LE) rc = launchT<MC_LE, false, 7, 7>(mp, b, failFlag, flags, st);
+        else if (elType == EWB_C3D8 && mc == MC_VM) rc = launchT<MC_VM, false, 7, 7>(mp, b, failFlag, flags, st);
+        else if (elType == EWB_C3D8TL && mc == MC_NH) rc = launchT<MC_NH, true, 7, 5>(mp, b, failFlag, flags, st);
         if (rc == EWB_OK) *launches = 1;
         return rc;
     }
