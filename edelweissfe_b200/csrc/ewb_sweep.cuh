@@ -9,13 +9,17 @@
 //     coalesced stores, each CSR value exactly once, no atomics, fixed summation order;
 //   * elements on the tile rim are recomputed by the neighbouring CTA (halo recompute), so there is
 //     no inter-CTA communication;
-//   * phase A (thread = element x Gauss point) is shared with the generic path (ewb_tile.cuh);
-//   * phase B runs on the FP64 tensor pipe: per element, M[(i,a),(j,b)] = sum_gp (c_gp g_a,i) g_b,j
-//     is a (24x8)x(8x24) product = 3x3 tiles of mma.m8n8k4.f64 with the tile index = component
-//     pair (i,j), so that every lane ends up with complete 3x3 node blocks and the isotropic /
-//     rank-one / Neo-Hooke tangent assembly is lane-local;
-//   * the 2x2 element patch of a warp has 4 different colours; all warps process the same colour
-//     between two barriers, so shared-memory accumulation is race free and deterministic.
+//   * phase A (lane = element x Gauss point, 4 elements of a 2x2 patch per warp): J, J^-1, strain
+//     increment / F, constitutive update, state write-back; publishes per Gauss point only J^-1, the
+//     tangent coefficients and -w detJ*stress (17..37 doubles) — grad N is rebuilt in phase B from J^-1
+//     and lane-constant shape-function derivatives;
+//   * phase B (one element per warp at a time) runs on the FP64 tensor pipe: M[(i,a),(j,b)] =
+//     sum_gp (c_gp g_a,i) g_b,j is a (24x8)x(8x24) product = 3x3 tiles of mma.m8n8k4.f64 with the tile
+//     index = component pair (i,j), so that every lane ends up with complete 3x3 node blocks and the
+//     isotropic / rank-one / Neo-Hooke tangent assembly is lane-local;
+//   * the 4 elements of a warp's patch have 4 different colours; an element of colour k is accumulated
+//     only after the 8 neighbouring patches finished colour k-1 (flags in shared memory, no CTA
+//     barrier), so shared-memory accumulation is race free and its order is fixed (deterministic).
 #pragma once
 #include "../../include/edelweiss_b200.h"
 #include "ewb_tile.cuh"
@@ -33,23 +37,24 @@ struct SweepArgs {
     double* data;
     double* P;
     double* F;
-    const int64_t* adjPtr;
     MatParams mp;
     int* failFlag;
     int wantK;
     int accumulatePF;
 };
 
+// Per-Gauss-point record published by phase A (doubles):
+//   LE: [0..8] J^-1 | [9] w detJ               | [10..15] -w detJ sigma
+//   VM: [0..8] J^-1 | [9..11] w(lam', mu', -a) | [12..17] -w detJ sigma | [18..23] n
+//   NH: [0..8] J^-1 | [9..12] w(c0,c1,c2,c4)   | [13..18] -w detJ tau   | [19..27] F^-1 | [28..36] F
+// odd record stride + element stride == 8 (mod 16): conflict-free phase-A stores.
 template <int MC>
-struct SweepLayout {
-    static constexpr bool HASQ = false;
-    static constexpr int GST = 28;  // == 4 (mod 16): conflict-free mma fragment loads (lane -> node 3a, gp 28k)
-    static constexpr int NCO = (MC == MC_LE) ? 10 : (MC == MC_VM ? 16 : 28);
-    static constexpr int OFF_G = 0;
-    static constexpr int OFF_Q = 0;
-    static constexpr int OFF_CO = 8 * GST;
-    static constexpr int RAW = OFF_CO + 8 * NCO;
-    static constexpr int PER_EL = RAW + ((2 - RAW % 16) + 16) % 16;  // == 2 (mod 16)
+struct RecLayout {
+    static constexpr int C_CO = 9;
+    static constexpr int C_S = (MC == MC_LE) ? 10 : (MC == MC_VM ? 12 : 13);
+    static constexpr int C_X = C_S + 6;  // VM: n ; NH: F^-1 then F
+    static constexpr int RS = (MC == MC_LE) ? 17 : (MC == MC_VM ? 25 : 37);
+    static constexpr int PER_EL = 8 * RS;
 };
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
@@ -64,22 +69,145 @@ __device__ __forceinline__ int ndz(int a) { return (a ^ (a >> 1)) & 1; }
 // mma row/column r  <->  local node ROWPERM[r] = {0,1,3,2,5,4,6,7}[r]  (fewest bank conflicts, see AccLayout)
 __device__ __forceinline__ int rowNode(int r) { return (0x76452310u >> (4 * r)) & 7; }
 
-// Phase B for ONE element by one warp: lane (r = lane>>2, q = lane&3) ends with the 3x3 stiffness blocks
-// K0 = K[node a][node b0], K1 = K[node a][node b1] (a = rowNode(lane>>2), b_t = rowNode(2q+t)) and (all 4 lanes
-// of a row) the residual row Pr of node a.
-// T: the element's shared-memory tables written by phase A.
+// ---------------------------------------------------------------------------------------------
+// phase A: one lane = one Gauss point of one element
+// ---------------------------------------------------------------------------------------------
+template <int MC, bool TL>
+__device__ __forceinline__ void gaussPointCompact(double* rec, const double* __restrict__ coords, const double* __restrict__ uSrc,
+                                                  const int (&nodeIdx)[8], int gp, const MatParams& mp,
+                                                  const double* __restrict__ state_ref, double* __restrict__ state_temp, int64_t cstride,
+                                                  bool writeState, int* failFlag) {
+    using R = RecLayout<MC>;
+    constexpr int NST = 12 + (MC != MC_LE ? 1 : 0);
+    double st[13];
+#pragma unroll
+    for (int c = 0; c < NST; ++c) st[c] = state_ref[c * cstride];
+
+    double xi, eta, zeta, w;
+    Gauss<8>::get(gp, xi, eta, zeta, w);
+    // J = sum_a dN_a (x) X_a ; D[i][r] = sum_a u_a[i] dN_a[r]  (local displacement gradient)
+    double Jm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double D[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    forNodes<8>([&](auto ic) {
+        constexpr int a = decltype(ic)::value;
+        double d[3];
+        shapeDeriv<8, a>(xi, eta, zeta, d);
+        const double* xp = coords + 3 * nodeIdx[a];
+        const double* up = uSrc + 3 * nodeIdx[a];
+        const double x0 = __ldg(xp), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
+        const double u0 = __ldg(up), u1 = __ldg(up + 1), u2 = __ldg(up + 2);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            Jm[r * 3 + 0] = fma(d[r], x0, Jm[r * 3 + 0]);
+            Jm[r * 3 + 1] = fma(d[r], x1, Jm[r * 3 + 1]);
+            Jm[r * 3 + 2] = fma(d[r], x2, Jm[r * 3 + 2]);
+            D[0 + r] = fma(u0, d[r], D[0 + r]);
+            D[3 + r] = fma(u1, d[r], D[3 + r]);
+            D[6 + r] = fma(u2, d[r], D[6 + r]);
+        }
+    });
+    const double detJ = det3(Jm);
+    double iJ[9];
+    inv3(Jm, detJ, iJ);
+    const double wd = w * detJ;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) rec[i] = iJ[i];
+    // H[i][c] = du_i/dx_c = sum_r D[i][r] iJ[c][r]
+    double H[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) H[i * 3 + c] = D[i * 3] * iJ[c * 3] + D[i * 3 + 1] * iJ[c * 3 + 1] + D[i * 3 + 2] * iJ[c * 3 + 2];
+
+    if constexpr (!TL) {
+        // Voigt 11,22,33,12,13,23 with engineering shear (_B3D8)
+        const double de[6] = {H[0], H[4], H[8], H[1] + H[3], H[2] + H[6], H[5] + H[7]};
+        double sg[6] = {st[0], st[1], st[2], st[3], st[4], st[5]};
+        if constexpr (MC == MC_LE) {
+            hookeAdd(mp, de, sg);
+            rec[R::C_CO] = wd;
+        } else {
+            VMResult r;
+            double kappa = st[12];
+            vonMises(mp, de, sg, kappa, r);
+            st[12] = kappa;
+            if (r.failed) atomicOr(failFlag, 1);
+            rec[R::C_CO] = wd * r.lam;
+            rec[R::C_CO + 1] = wd * r.mu;
+            rec[R::C_CO + 2] = -wd * r.a;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) rec[R::C_X + i] = r.n[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) rec[R::C_S + i] = -wd * sg[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            st[i] = sg[i];
+            st[6 + i] += de[i];
+        }
+    } else {
+        double F[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) F[i] = H[i];
+        F[0] += 1.0;
+        F[4] += 1.0;
+        F[8] += 1.0;
+        const double Jf = det3(F);
+        double iF[9];
+        inv3(F, Jf, iF);
+        NHResult r;
+        neoHooke(mp, F, Jf, r);
+        rec[R::C_CO] = wd * r.c0;
+        rec[R::C_CO + 1] = wd * r.c1;
+        rec[R::C_CO + 2] = wd * r.c2;
+        rec[R::C_CO + 3] = wd * r.c4;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) rec[R::C_S + i] = -wd * r.tau[i];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) rec[R::C_X + i] = iF[i];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) rec[R::C_X + 9 + i] = F[i];
+        // Kirchhoff stress Voigt 11,22,33,12,23,13 ; Green-Lagrange strain with doubled shear (voigtnotation.py)
+        st[0] = r.tau[0];
+        st[1] = r.tau[1];
+        st[2] = r.tau[2];
+        st[3] = r.tau[3];
+        st[4] = r.tau[5];
+        st[5] = r.tau[4];
+        st[6] = H[0] + 0.5 * (H[0] * H[0] + H[3] * H[3] + H[6] * H[6]);
+        st[7] = H[4] + 0.5 * (H[1] * H[1] + H[4] * H[4] + H[7] * H[7]);
+        st[8] = H[8] + 0.5 * (H[2] * H[2] + H[5] * H[5] + H[8] * H[8]);
+        st[9] = H[1] + H[3] + H[0] * H[1] + H[3] * H[4] + H[6] * H[7];
+        st[10] = H[5] + H[7] + H[1] * H[2] + H[4] * H[5] + H[7] * H[8];
+        st[11] = H[2] + H[6] + H[0] * H[2] + H[3] * H[5] + H[6] * H[8];
+        st[12] = r.energy;
+    }
+    if (writeState) {
+#pragma unroll
+        for (int c = 0; c < NST; ++c) state_temp[c * cstride] = st[c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase B for ONE element by one warp.  Lane (row = lane>>2, q = lane&3), a = rowNode(row), b_t =
+// rowNode(2q+t): returns K0 = K[a][b_0], K1 = K[a][b_1] and (in all 4 lanes of the row) the residual
+// row Pr of node a.  dNl[ks][r]: lane-constant dN_a/d(eta,xi,zeta) at Gauss point 4ks+q.
+// ---------------------------------------------------------------------------------------------
 template <int MC>
-__device__ __forceinline__ void elementBlocks(const double* T, int lane, const MatParams& mp, bool wantK, double (&K0)[9], double (&K1)[9],
-                                              double (&Pr)[3]) {
-    using L = SweepLayout<MC>;
-    const int r = rowNode(lane >> 2), q = lane & 3;
+__device__ __forceinline__ void elementBlocks(const double* T, int lane, const double (&dNl)[2][3], const MatParams& mp, bool wantK,
+                                              double (&K0)[9], double (&K1)[9], double (&Pr)[3]) {
+    using R = RecLayout<MC>;
+    const int q = lane & 3;
     double g[2][3];
     Pr[0] = Pr[1] = Pr[2] = 0.0;
+    const double* rec0 = T + q * R::RS;
+    const double* rec1 = T + (4 + q) * R::RS;
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks)
+    for (int ks = 0; ks < 2; ++ks) {
+        const double* rec = ks ? rec1 : rec0;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) g[ks][c] = T[L::OFF_G + (4 * ks + q) * L::GST + r * 3 + c];
-    // residual row partial: (-w detJ S) v_r over this lane's two Gauss points
+        for (int c = 0; c < 3; ++c) g[ks][c] = rec[c * 3] * dNl[ks][0] + rec[c * 3 + 1] * dNl[ks][1] + rec[c * 3 + 2] * dNl[ks][2];
+    }
     if constexpr (MC == MC_LE) {
         double c[3][3][2];
 #pragma unroll
@@ -88,9 +216,9 @@ __device__ __forceinline__ void elementBlocks(const double* T, int lane, const M
             for (int j = 0; j < 3; ++j) c[i][j][0] = c[i][j][1] = 0.0;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-            const double* co = T + L::OFF_CO + (4 * ks + q) * L::NCO;
-            const double w = co[0];
-            const double* S = co + 4;
+            const double* rec = ks ? rec1 : rec0;
+            const double w = rec[R::C_CO];
+            const double* S = rec + R::C_S;
             Pr[0] += S[0] * g[ks][0] + S[3] * g[ks][1] + S[4] * g[ks][2];
             Pr[1] += S[3] * g[ks][0] + S[1] * g[ks][1] + S[5] * g[ks][2];
             Pr[2] += S[4] * g[ks][0] + S[5] * g[ks][1] + S[2] * g[ks][2];
@@ -103,14 +231,21 @@ __device__ __forceinline__ void elementBlocks(const double* T, int lane, const M
                 }
             }
         }
+        const double lpm = mp.lambda + mp.G;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             double* Kt = t ? K1 : K0;
             const double tr = mp.G * (c[0][0][t] + c[1][1][t] + c[2][2][t]);
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < 3; ++i) {
+                Kt[i * 3 + i] = fma(lpm, c[i][i][t], tr);
 #pragma unroll
-                for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = mp.lambda * c[i][j][t] + mp.G * c[j][i][t] + (i == j ? tr : 0.0);
+                for (int j = i + 1; j < 3; ++j) {
+                    const double x = c[i][j][t], y = c[j][i][t];
+                    Kt[i * 3 + j] = fma(mp.lambda, x, mp.G * y);
+                    Kt[j * 3 + i] = fma(mp.lambda, y, mp.G * x);
+                }
+            }
         }
     } else if constexpr (MC == MC_VM) {
         double c1[3][3][2], c2[3][3][2];
@@ -120,14 +255,15 @@ __device__ __forceinline__ void elementBlocks(const double* T, int lane, const M
             for (int j = 0; j < 3; ++j) c1[i][j][0] = c1[i][j][1] = c2[i][j][0] = c2[i][j][1] = 0.0;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-            const double* co = T + L::OFF_CO + (4 * ks + q) * L::NCO;
-            const double cl = co[0], cm = co[1], ca = co[2];
-            const double* S = co + 4;
-            const double* n = co + 10;
+            const double* rec = ks ? rec1 : rec0;
+            const double cl = rec[R::C_CO], cm = rec[R::C_CO + 1], ca = rec[R::C_CO + 2];
+            const double* S = rec + R::C_S;
+            const double* n = rec + R::C_X;
             Pr[0] += S[0] * g[ks][0] + S[3] * g[ks][1] + S[4] * g[ks][2];
             Pr[1] += S[3] * g[ks][0] + S[1] * g[ks][1] + S[5] * g[ks][2];
             Pr[2] += S[4] * g[ks][0] + S[5] * g[ks][1] + S[2] * g[ks][2];
             if (wantK) {
+                // p_a = B_a^T n = N g_a, N = tensor(n)  (n Voigt 11,22,33,12,13,23)
                 double pv[3];
                 pv[0] = n[0] * g[ks][0] + n[3] * g[ks][1] + n[4] * g[ks][2];
                 pv[1] = n[3] * g[ks][0] + n[1] * g[ks][1] + n[5] * g[ks][2];
@@ -164,12 +300,12 @@ __device__ __forceinline__ void elementBlocks(const double* T, int lane, const M
         const bool wb = (mp.kind == EWB_MAT_NEOHOOKE_WB);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-            const double* co = T + L::OFF_CO + (4 * ks + q) * L::NCO;
-            const double k0 = co[0], k1 = co[1], k2 = co[2], k4 = co[3];
-            const double* S = co + 4;
-            const double* F = co + 10;
-            const double* iF = co + 19;
-            double nv[3];
+            const double* rec = ks ? rec1 : rec0;
+            const double k0 = rec[R::C_CO], k1 = rec[R::C_CO + 1], k2 = rec[R::C_CO + 2], k4 = rec[R::C_CO + 3];
+            const double* S = rec + R::C_S;
+            const double* iF = rec + R::C_X;
+            const double* F = rec + R::C_X + 9;
+            double nv[3];  // n_a = F^-T grad N_a
 #pragma unroll
             for (int m = 0; m < 3; ++m) nv[m] = g[ks][0] * iF[m] + g[ks][1] * iF[3 + m] + g[ks][2] * iF[6 + m];
             Pr[0] += S[0] * nv[0] + S[3] * nv[1] + S[4] * nv[2];
@@ -186,7 +322,7 @@ __device__ __forceinline__ void elementBlocks(const double* T, int lane, const M
                         dmma(c2[i][j], a2, nv[j]);
                     }
                 }
-                if (wb) {  // W_b: + c4 (f_a n_b^T + n_a f_b^T), f = F g
+                if (wb) {  // W_b: + c4 (f_a n_b^T + n_a f_b^T), f = F grad N
                     double fv[3];
 #pragma unroll
                     for (int i = 0; i < 3; ++i) fv[i] = F[i * 3] * g[ks][0] + F[i * 3 + 1] * g[ks][1] + F[i * 3 + 2] * g[ks][2];
@@ -210,148 +346,18 @@ __device__ __forceinline__ void elementBlocks(const double* T, int lane, const M
                 for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = c1[i][j][t] + c2[j][i][t] + (i == j ? tr : 0.0);
         }
     }
-    // reduce the residual row over the 4 lanes (Gauss-point pairs) of node r
+    // reduce the residual row over the 4 lanes (Gauss-point pairs) of the row
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         Pr[i] += __shfl_xor_sync(0xffffffffu, Pr[i], 1);
         Pr[i] += __shfl_xor_sync(0xffffffffu, Pr[i], 2);
-    }}
-
-// Phase A for Hexa8 with TWO lanes per (element, Gauss point): lane half h handles the nodes
-// a = a' + 4h (a' = 0..3; the two xi-faces of the element), partial J and displacement gradients are
-// combined with one butterfly shuffle.  Halves the registers per thread (so that 16 warps fit) and the
-// number of elements a warp has in flight (2), at the price of a redundant 3x3 inverse + material update.
-template <class L, int MC, bool TL>
-__device__ __forceinline__ void gaussPointHalf(double* sm, const double (&Xh)[12], const double (&uh)[12], int gp, int h, unsigned mask,
-                                               const MatParams& mp, const double* __restrict__ state_ref, double* __restrict__ state_temp,
-                                               int64_t cstride, bool writeState, int* failFlag) {
-    double* G = sm + L::OFF_G + gp * L::GST + 12 * h;
-    double* CO = sm + L::OFF_CO + gp * L::NCO;
-    constexpr int NST = 12 + (MC != MC_LE ? 1 : 0);
-    double st[13];
-#pragma unroll
-    for (int c = 0; c < NST; ++c) st[c] = state_ref[c * cstride];
-
-    double xi, eta, zeta, w;
-    Gauss<8>::get(gp, xi, eta, zeta, w);
-    const double sx = h ? 1.0 : -1.0;
-    const double fx = 1.0 + sx * xi;
-    double dN[4][3];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const double be = NodeLC<8>::eta(a), cz = NodeLC<8>::zeta(a);  // eta/zeta signs do not depend on h
-        const double fe = 1.0 + be * eta, fz = 1.0 + cz * zeta;
-        dN[a][0] = 0.125 * be * fx * fz;
-        dN[a][1] = 0.125 * sx * fe * fz;
-        dN[a][2] = 0.125 * cz * fx * fe;
-    }
-    double Jm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) Jm[r * 3 + c] = fma(dN[a][r], Xh[a * 3 + c], Jm[r * 3 + c]);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) Jm[i] += __shfl_xor_sync(mask, Jm[i], 1);
-    const double detJ = det3(Jm);
-    double iJ[9];
-    inv3(Jm, detJ, iJ);
-    const double wd = w * detJ;
-    double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        double g[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) g[c] = iJ[c * 3 + 0] * dN[a][0] + iJ[c * 3 + 1] * dN[a][1] + iJ[c * 3 + 2] * dN[a][2];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) G[a * 3 + c] = g[c];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) H[i * 3 + c] = fma(uh[a * 3 + i], g[c], H[i * 3 + c]);
-    }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) H[i] += __shfl_xor_sync(mask, H[i], 1);
-
-    // both half-lanes run the (cheap) constitutive update; lane h == 0 publishes it
-    if constexpr (!TL) {
-        const double de[6] = {H[0], H[4], H[8], H[1] + H[3], H[2] + H[6], H[5] + H[7]};
-        double sg[6] = {st[0], st[1], st[2], st[3], st[4], st[5]};
-        if constexpr (MC == MC_LE) {
-            hookeAdd(mp, de, sg);
-            if (h == 0) CO[0] = wd;
-        } else {
-            VMResult r;
-            double kappa = st[12];
-            vonMises(mp, de, sg, kappa, r);
-            st[12] = kappa;
-            if (h == 0) {
-                if (r.failed) atomicOr(failFlag, 1);
-                CO[0] = wd * r.lam;
-                CO[1] = wd * r.mu;
-                CO[2] = -wd * r.a;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) CO[10 + i] = r.n[i];
-            }
-        }
-        if (h == 0) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) CO[4 + i] = -wd * sg[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            st[i] = sg[i];
-            st[6 + i] += de[i];
-        }
-    } else {
-        double F[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) F[i] = H[i];
-        F[0] += 1.0;
-        F[4] += 1.0;
-        F[8] += 1.0;
-        const double Jf = det3(F);
-        double iF[9];
-        inv3(F, Jf, iF);
-        NHResult r;
-        neoHooke(mp, F, Jf, r);
-        if (h == 0) {
-            CO[0] = wd * r.c0;
-            CO[1] = wd * r.c1;
-            CO[2] = wd * r.c2;
-            CO[3] = wd * r.c4;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) CO[4 + i] = -wd * r.tau[i];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) CO[10 + i] = F[i];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) CO[19 + i] = iF[i];
-        }
-        st[0] = r.tau[0];
-        st[1] = r.tau[1];
-        st[2] = r.tau[2];
-        st[3] = r.tau[3];
-        st[4] = r.tau[5];
-        st[5] = r.tau[4];
-        st[6] = H[0] + 0.5 * (H[0] * H[0] + H[3] * H[3] + H[6] * H[6]);
-        st[7] = H[4] + 0.5 * (H[1] * H[1] + H[4] * H[4] + H[7] * H[7]);
-        st[8] = H[8] + 0.5 * (H[2] * H[2] + H[5] * H[5] + H[8] * H[8]);
-        st[9] = H[1] + H[3] + H[0] * H[1] + H[3] * H[4] + H[6] * H[7];
-        st[10] = H[5] + H[7] + H[1] * H[2] + H[4] * H[5] + H[7] * H[8];
-        st[11] = H[2] + H[6] + H[0] * H[2] + H[3] * H[5] + H[6] * H[8];
-        st[12] = r.energy;
-    }
-    if (writeState && h == 0) {
-#pragma unroll
-        for (int c = 0; c < NST; ++c) state_temp[c * cstride] = st[c];
     }
 }
 
 // Accumulator geometry (doubles).  Per node column 81 doubles per segment, laid out [i][s9][j] so that a
 // CSR sub-row (27 values) is contiguous.  The four segment bases sit at residues 0,7,8,15 (mod 16 doubles)
-// and the mma rows are permuted (ROWPERM) — together the cheapest bank pattern found by exhaustive search
-// for the accumulation stores (tools/bank_search.py): 1.5 wavefronts per half-warp instead of 3.0.
+// and the mma rows are permuted (rowNode) — together the cheapest bank pattern found by exhaustive search
+// for the accumulation stores: 1.5 wavefronts per half-warp instead of 3.0.
 __host__ __device__ constexpr int alignRes(int x, int r) { return x + ((r - x % 16) + 16) % 16; }
 template <int TY, int TZ>
 struct AccLayout {
@@ -376,19 +382,18 @@ __device__ __forceinline__ void waitFlags(const volatile int* flag, int dep, boo
     while (true) {
         const bool ok = !has || flag[dep] >= target;
         if (__all_sync(0xffffffffu, ok)) break;
-        if (++spins > (1 << 22)) {
+        if (++spins > (1 << 24)) {
             atomicOr(failFlag, 4);
             break;
         }
-        __nanosleep(20);
     }
     __threadfence_block();
 }
 
-// One warp per 2x2 element patch; NW == number of patches of the tile.
+// One warp per 2x2 element patch; number of warps == number of patches of the tile.
 template <int MC, bool TL, int TY, int TZ>
 __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweepKernel(const SweepArgs A) {
-    using L = SweepLayout<MC>;
+    using R = RecLayout<MC>;
     using AL = AccLayout<TY, TZ>;
     constexpr int NPY = (TY + 1) / 2, NPZ = (TZ + 1) / 2, NW = NPY * NPZ;
     constexpr int NCOL = TY * TZ;
@@ -406,10 +411,10 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
     double* pfB = pfA + NCOL * 6;       // upper plane
     int* colPart = reinterpret_cast<int*>(smem + AL::INFO);
     int* colCycz = colPart + NCOL;
-    int* laneOff = colCycz + NCOL;      // [NCOL][32]
+    int* laneOff = colCycz + NCOL;                // [NCOL][32]
     volatile int* doneCnt = laneOff + NCOL * 32;  // [32] rounds completed per patch
     volatile int* flushedCnt = doneCnt + 32;      // [32] plane steps flushed per patch
-    double* tables = smem + AL::TABLES; // [NW][2][PER_EL]
+    double* tables = smem + AL::TABLES;           // [NW][4][PER_EL]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NX = A.nX + 1, NY = A.nY + 1, NZ = A.nZ + 1;
@@ -427,7 +432,7 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
     for (int i = tid; i < AL::INFO; i += NT) smem[i] = 0.0;
     if (tid < 64) doneCnt[tid] = 0;
     // CSR row base of node (ix,iy,iz) in closed form: 9 * (sum of the degrees of all preceding nodes);
-    // deg = cx*cy*cz with c = 2 on a face, 3 inside (== plan->adjPtr, checked by the parity tests).
+    // deg = cx*cy*cz with c = 2 on a face, 3 inside (== the plan's node adjacency, checked by the parity tests).
     // base = 9 * (pre(ix)*totY*totZ + cx * colPart),  colPart = pre(iy)*totZ + cy*pre(iz).
     auto pre = [](int i) { return i == 0 ? 0 : 3 * i - 1; };
     const int totY = 3 * NY - 2, totZ = 3 * NZ - 2;
@@ -454,17 +459,18 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
     const int64_t cstride = (int64_t)A.nX * A.nY * A.nZ * 8;
     const double* __restrict__ uSrc = TL ? A.U : A.dU;
     const int64_t totYZ = (int64_t)totY * totZ;
+    const int strideX = NY * NZ;
 
     // this warp's patch and its dependencies
     const int p = warp, pyq = p / NPZ, pzq = p % NPZ;
-    // (1) emission of round R waits for the 8 neighbouring patches to have finished round R-1
+    // (1) accumulation of round R waits for the 8 neighbouring patches to have finished round R-1
     int depN = 0; bool hasN = false;
     if (lane < 9) {
         const int qy = pyq + lane / 3 - 1, qz = pzq + lane % 3 - 1;
         hasN = lane != 4 && qy >= 0 && qy < NPY && qz >= 0 && qz < NPZ;
         depN = hasN ? qy * NPZ + qz : 0;
     }
-    // (2) the first emission of a plane step waits for the owners of the columns it touches to have flushed the previous step
+    // (2) the first accumulation of a plane step waits for the owners of the columns it touches to have flushed the previous step
     int depF = 0; bool hasF = false;
     if (lane < 4) {
         const int qy = pyq - (lane >> 1), qz = pzq - (lane & 1);
@@ -479,10 +485,36 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
         depD = hasD ? qy * NPZ + qz : 0;
     }
 
+    // ---- lane constants of phase B ----
+    const int bRow = lane >> 2, bq = lane & 3;
+    const int na = rowNode(bRow);  // node of this lane's mma row
+    double dNl[2][3];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        double xi, eta, zeta, w;
+        Gauss<8>::get(4 * ks + bq, xi, eta, zeta, w);
+        const double sa = NodeLC<8>::xi(na), sb = NodeLC<8>::eta(na), sc = NodeLC<8>::zeta(na);
+        const double fx = 1.0 + sa * xi, fe = 1.0 + sb * eta, fz = 1.0 + sc * zeta;
+        dNl[ks][0] = 0.125 * sb * fx * fz;
+        dNl[ks][1] = 0.125 * sa * fe * fz;
+        dNl[ks][2] = 0.125 * sc * fx * fe;
+    }
+    // accumulation targets of the two blocks of this lane: segment selector and offset inside the tile image
+    int accOff[2];
+    bool accSame[2];  // block stays in the node plane of a (dx = 0 segment) or crosses to the other plane
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int nb = rowNode(2 * bq + t);
+        const int ry = ndy(nb) - ndy(na), rz = ndz(nb) - ndz(na);
+        accSame[t] = ndx(nb) == ndx(na);
+        accOff[t] = (ndy(na) * TZ + ndz(na)) * CS + ((ry + 1) * 3 + rz + 1) * 3;
+    }
+    const bool aHi = ndx(na) != 0;
+
     // flush the finished segments (nullptr = not finished) of this warp's owned nodes of plane ix, clear them
     auto flushPlane = [&](int ix, double* sM, double* s0, double* sP, double* pf) {
         const int cx = (ix > 0) + 1 + (ix < NX - 1);
-        const int64_t xbase = (int64_t)pre(ix) * totYZ;
+        const int64_t xbase = 9 * (int64_t)pre(ix) * totYZ;
         const int rx0 = ix > 0 ? 1 : 0;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
@@ -492,24 +524,22 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
             const int cycz = colCycz[col];
             if (cycz == 0) continue;
             const int lo = laneOff[col * 32 + lane];
-            const int64_t base = 9 * (xbase + (int64_t)cx * colPart[col]);
-            const int64_t rowStride = 3 * cx * cycz;
-            if (A.wantK) {
+            double* rowBase = A.data + (xbase + (int64_t)(9 * cx) * colPart[col] + lo);
+            const int rowStride = 3 * cx * cycz;
+            if (A.wantK && lane < 27) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                     double* seg = d == 0 ? sM : (d == 1 ? s0 : sP);
                     if (seg == nullptr) continue;
                     const int dx = d - 1;
-                    const bool dxValid = ix + dx >= 0 && ix + dx < NX;
-                    if (lane < 27) {
-                        double* src = seg + col * CS + lane;
-                        double* dst = A.data + base + 3 * ((dx + rx0) * cycz) + lo;
+                    const bool ok = ix + dx >= 0 && ix + dx < NX && lo >= 0;
+                    double* src = seg + col * CS + lane;
+                    double* dst = rowBase + 3 * ((dx + rx0) * cycz);
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) {
-                            const double v = src[i * 27];
-                            src[i * 27] = 0.0;
-                            if (dxValid && lo >= 0) dst[i * rowStride] = v;
-                        }
+                    for (int i = 0; i < 3; ++i) {
+                        const double v = src[i * 27];
+                        src[i * 27] = 0.0;
+                        if (ok) dst[i * rowStride] = v;
                     }
                 }
             }
@@ -529,87 +559,75 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
         }
     };
 
-    double* wt = tables + (size_t)warp * 2 * L::PER_EL;
+    double* wt = tables + (size_t)warp * 4 * R::PER_EL;
+    // phase-A lane constants: element k of the patch, Gauss point
+    const int ak = lane >> 3, agp = lane & 7;
+    const int apy = 2 * pyq + (ak >> 1), apz = 2 * pzq + (ak & 1);
+    const int aey = y0 - 1 + apy, aez = z0 - 1 + apz;
+    const bool aValid = aey >= 0 && aey < A.nY && aez >= 0 && aez < A.nZ && apy <= ny && apz <= nz;
+
     int step = 0;
     for (int ex = exBegin; ex <= exEnd; ++ex, ++step) {
         const bool loOwned = ex >= xa, hiOwned = (ex + 1) < xb;
+        // ------------- phase A: the 4 elements of the patch -------------
+        if (aValid) {
+            int nodeIdx[8];
+            const int n0 = (ex * NY + aey) * NZ + aez;
+#pragma unroll
+            for (int a = 0; a < 8; ++a) nodeIdx[a] = n0 + ndx(a) * strideX + ndy(a) * NZ + ndz(a);
+            const int64_t e = ((int64_t)ex * A.nY + aey) * A.nZ + aez;
+            const int64_t off = e * 8 + agp;
+            const bool writeState = loOwned && apy >= 1 && apz >= 1;
+            gaussPointCompact<MC, TL>(wt + ak * R::PER_EL + agp * R::RS, A.coords, uSrc, nodeIdx, agp, A.mp, A.stateRef + off, A.stateTemp + off,
+                                      cstride, writeState, A.failFlag);
+        }
+        __syncwarp();
+        // per-step accumulation bases of this lane (segments rotate every plane)
+        double* accBase[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) accBase[t] = (aHi ? (accSame[t] ? hi0 : segM) : (accSame[t] ? lo0 : segP)) + accOff[t];
+        double* pfBase = (aHi ? pfHi : pfLo) + (ndy(na) * TZ + ndz(na)) * 6;
+        const bool planeOwned = aHi ? hiOwned : loOwned;
+        // ------------- phase B: 4 colour rounds, one element per round -------------
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            // ------------- phase A: lane = (element slot e2, Gauss point, node half) -------------
-            {
-                const int e2 = lane >> 4, gp = (lane >> 1) & 7, h = lane & 1;
-                const int k = 2 * pass + e2;  // colour = position in the 2x2 patch
-                const int py = 2 * pyq + (k >> 1), pz = 2 * pzq + (k & 1);
-                const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
-                const bool valid = ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz;
-                if (valid) {
-                    double Xh[12], uh[12];
+        for (int k = 0; k < 4; ++k) {
+            const int Rnd = 4 * step + k;
+            const int py = 2 * pyq + (k >> 1), pz = 2 * pzq + (k & 1);
+            const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
+            const bool valid = ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz;
+            // ---- ordering: same-colour elements of different patches never share a node ----
+            if (k == 0) waitFlags(flushedCnt, depF, hasF, step, A.failFlag);
+            waitFlags(doneCnt, depN, hasN, Rnd, A.failFlag);
+            double K0[9], K1[9], Pr[3];
+            if (valid) elementBlocks<MC>(wt + k * R::PER_EL, lane, dNl, A.mp, A.wantK != 0, K0, K1, Pr);
+            if (valid) {
+                const int ly = py - 1 + ndy(na), lz = pz - 1 + ndz(na);
+                if (planeOwned && ly >= 0 && ly < ny && lz >= 0 && lz < nz) {
+                    const int eOff = (py - 1) * TZ + (pz - 1);
+                    if (bq == 0) {
+                        double* pf = pfBase + eOff * 6;
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        // node a + 4h: dy = h, (dx,dz) of a
-                        const int64_t n = ((int64_t)(ex + ndx(a)) * NY + (ey + h)) * NZ + (ez + ndz(a));
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            Xh[a * 3 + c] = __ldg(A.coords + 3 * n + c);
-                            uh[a * 3 + c] = __ldg(uSrc + 3 * n + c);
+                        for (int i = 0; i < 3; ++i) {
+                            pf[i] += Pr[i];
+                            pf[3 + i] += fabs(Pr[i]);
                         }
                     }
-                    const int64_t e = ((int64_t)ex * A.nY + ey) * A.nZ + ez;
-                    const int64_t off = e * 8 + gp;
-                    const bool writeState = loOwned && py >= 1 && pz >= 1;
-                    gaussPointHalf<L, MC, TL>(wt + e2 * L::PER_EL, Xh, uh, gp, h, 0xffffu << (16 * e2), A.mp, A.stateRef + off, A.stateTemp + off,
-                                              cstride, writeState, A.failFlag);
+                    if (A.wantK) {
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            double* dst = accBase[t] + eOff * CS;
+                            const double* Kt = t ? K1 : K0;
+#pragma unroll
+                            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                                for (int j = 0; j < 3; ++j) dst[i * 27 + j] += Kt[i * 3 + j];
+                        }
+                    }
                 }
             }
+            __threadfence_block();
             __syncwarp();
-            // ------------- phase B: 2 colour rounds, one element per round -------------
-#pragma unroll 1
-            for (int rr = 0; rr < 2; ++rr) {
-                const int k = 2 * pass + rr;
-                const int R = 4 * step + k;
-                const int py = 2 * pyq + (k >> 1), pz = 2 * pzq + (k & 1);
-                const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
-                const bool valid = ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz;
-                double K0[9], K1[9], Pr[3];
-                if (valid) elementBlocks<MC>(wt + rr * L::PER_EL, lane, A.mp, A.wantK != 0, K0, K1, Pr);
-                // ---- ordering: same-colour elements of different patches never share a node ----
-                if (k == 0) waitFlags(flushedCnt, depF, hasF, step, A.failFlag);
-                waitFlags(doneCnt, depN, hasN, R, A.failFlag);
-                if (valid) {
-                    // ---- accumulate into the owned rows ----
-                    const int a = rowNode(lane >> 2), q = lane & 3;
-                    const int ly = py - 1 + ndy(a), lz = pz - 1 + ndz(a);
-                    const bool owned = ly >= 0 && ly < ny && lz >= 0 && lz < nz && (ndx(a) ? hiOwned : loOwned);
-                    if (owned) {
-                        const int col = ly * TZ + lz;
-                        if (q == 0) {
-                            double* pf = (ndx(a) ? pfHi : pfLo) + col * 6;
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                pf[i] += Pr[i];
-                                pf[3 + i] += fabs(Pr[i]);
-                            }
-                        }
-                        if (A.wantK) {
-#pragma unroll
-                            for (int t = 0; t < 2; ++t) {
-                                const int b = rowNode(2 * q + t);
-                                const int rx = ndx(b) - ndx(a), ry = ndy(b) - ndy(a), rz = ndz(b) - ndz(a);
-                                double* seg = ndx(a) ? (rx == 0 ? hi0 : segM) : (rx == 0 ? lo0 : segP);
-                                double* dst = seg + col * CS + ((ry + 1) * 3 + rz + 1) * 3;
-                                const double* Kt = t ? K1 : K0;
-#pragma unroll
-                                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                                    for (int j = 0; j < 3; ++j) dst[i * 27 + j] += Kt[i * 3 + j];
-                            }
-                        }
-                    }
-                }
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) doneCnt[p] = R + 1;
-            }
+            if (lane == 0) doneCnt[p] = Rnd + 1;
         }
         // ---------------- flush this warp's finished columns, rotate ----------------
         waitFlags(doneCnt, depD, hasD, 4 * (step + 1), A.failFlag);
@@ -628,18 +646,23 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
 
 struct SweepPlan {
     int64_t nX = 0, nY = 0, nZ = 0;
-    const int64_t* adjPtr = nullptr;
+    const int64_t* adjPtr = nullptr;  // unused by the kernel (closed-form row bases); kept for debugging
     int nSM = 148;
 
     int build(int64_t nx, int64_t ny, int64_t nz) {
         nX = nx; nY = ny; nZ = nz;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
+        if (nSM <= 0) nSM = 148;
         return 0;
     }
     void release() {}
 
     template <int MC, bool TL, int TY, int TZ>
     int launchT(const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st) {
-        using Lay = SweepLayout<MC>;
+        using Rec = RecLayout<MC>;
+        if ((nX + 1) * (nY + 1) * (nZ + 1) >= ((int64_t)1 << 31) / 3) return EWB_ERR_UNSUPPORTED;  // int32 node indexing inside the kernel
         SweepArgs a;
         a.nX = (int)nX; a.nY = (int)nY; a.nZ = (int)nZ;
         a.tilesY = (int)((nY + 1 + TY - 1) / TY);
@@ -657,12 +680,12 @@ struct SweepPlan {
         a.chunkLen = (int)((nX + 1 + best - 1) / best);
         a.nChunks = (int)((nX + 1 + a.chunkLen - 1) / a.chunkLen);
         a.coords = b->coords; a.U = b->U; a.dU = b->dU; a.stateRef = b->state_ref; a.stateTemp = b->state_temp;
-        a.data = b->csr_data; a.P = b->P; a.F = b->F; a.adjPtr = adjPtr; a.mp = mp; a.failFlag = failFlag;
+        a.data = b->csr_data; a.P = b->P; a.F = b->F; a.mp = mp; a.failFlag = failFlag;
         a.wantK = (flags & EWB_FLAG_NO_STIFFNESS) ? 0 : 1;
         a.accumulatePF = (flags & EWB_FLAG_ACCUMULATE_PF) ? 1 : 0;
         constexpr int NW = ((TY + 1) / 2) * ((TZ + 1) / 2);
         auto kern = sweepKernel<MC, TL, TY, TZ>;
-        const size_t smem = ((size_t)AccLayout<TY, TZ>::TABLES + (size_t)NW * 2 * Lay::PER_EL) * sizeof(double);
+        const size_t smem = ((size_t)AccLayout<TY, TZ>::TABLES + (size_t)NW * 4 * Rec::PER_EL) * sizeof(double);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EWB_ERR_CUDA;
         const int64_t grid = tiles * a.nChunks;
         kern<<<(unsigned)grid, NW * 32, smem, st>>>(a);
@@ -672,7 +695,7 @@ struct SweepPlan {
     int launch(int elType, int mc, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st, int* launches) {
         int rc = EWB_ERR_UNSUPPORTED;
         if (elType == EWB_C3D8 && mc == MC_LE) rc = launchT<MC_LE, false, 7, 7>(mp, b, failFlag, flags, st);
-        else if (elType == EWB_C3D8 && mc == MC_VM) rc = launchT<MC_VM, false, 7, 7>(mp, b, failFlag, flags, st);
+        else if (elType == EWB_C3D8 && mc == MC_VM) rc = launchT<MC_VM, false, 7, 5>(mp, b, failFlag, flags, st);
         else if (elType == EWB_C3D8TL && mc == MC_NH) rc = launchT<MC_NH, true, 7, 5>(mp, b, failFlag, flags, st);
         if (rc == EWB_OK) *launches = 1;
         return rc;
