@@ -142,7 +142,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        res = cpu_reference_leg(args.workload, args.cpu_sample, max(1, min(args.steps, 3)), 1)
+        res = cpu_reference_leg(args.workload, args.cpu_sample, max(1, args.steps), max(1, min(args.warmup, 2)))
         line = {
             "impl": "reference", "metric": "Hexa8 K+P assembly throughput", "value": res["value"], "unit": "Melem/s", "n_gpus": args.gpus,
             "steps": res["steps"], "warmup": res["warmup"], "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -265,7 +265,7 @@ def main():
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu:
-        res = cpu_reference_leg(args.workload, args.cpu_sample, 1, 0)
+        res = cpu_reference_leg(args.workload, args.cpu_sample, 20, 1)
         line["cpu_baseline"] = {"value": res["value"], "unit": "Melem/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]}
     print(json.dumps(line))
     if world > 1:

@@ -4,6 +4,7 @@
 // every compute entry point launches CUDA kernels or fails.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>

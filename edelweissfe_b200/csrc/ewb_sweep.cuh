@@ -41,6 +41,7 @@ struct SweepArgs {
     int* failFlag;
     int wantK;
     int accumulatePF;
+    int spinNs;  // back-off of the flag polling loops (tuning knob, EWB_SPIN_NS)
 };
 
 // Per-Gauss-point record published by phase A (doubles):
@@ -377,15 +378,16 @@ struct AccLayout {
 
 // Warp-level wait until flag[dep] >= target for up to 9 dependencies (lane i polls dependency i).
 // Bounded: a logic error sets bit 2 of the status word instead of hanging the GPU.
-__device__ __forceinline__ void waitFlags(const volatile int* flag, int dep, bool has, int target, int* failFlag) {
+__device__ __forceinline__ void waitFlags(const volatile int* flag, int dep, bool has, int target, int* failFlag, int spinNs) {
     int spins = 0;
     while (true) {
         const bool ok = !has || flag[dep] >= target;
         if (__all_sync(0xffffffffu, ok)) break;
-        if (++spins > (1 << 24)) {
+        if (++spins > (1 << 22)) {
             atomicOr(failFlag, 4);
             break;
         }
+        if (spinNs > 0) __nanosleep(spinNs);
     }
     __threadfence_block();
 }
@@ -596,8 +598,8 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
             const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
             const bool valid = ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz;
             // ---- ordering: same-colour elements of different patches never share a node ----
-            if (k == 0) waitFlags(flushedCnt, depF, hasF, step, A.failFlag);
-            waitFlags(doneCnt, depN, hasN, Rnd, A.failFlag);
+            if (k == 0) waitFlags(flushedCnt, depF, hasF, step, A.failFlag, A.spinNs);
+            waitFlags(doneCnt, depN, hasN, Rnd, A.failFlag, A.spinNs);
             double K0[9], K1[9], Pr[3];
             if (valid) elementBlocks<MC>(wt + k * R::PER_EL, lane, dNl, A.mp, A.wantK != 0, K0, K1, Pr);
             if (valid) {
@@ -630,7 +632,7 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
             if (lane == 0) doneCnt[p] = Rnd + 1;
         }
         // ---------------- flush this warp's finished columns, rotate ----------------
-        waitFlags(doneCnt, depD, hasD, 4 * (step + 1), A.failFlag);
+        waitFlags(doneCnt, depD, hasD, 4 * (step + 1), A.failFlag, A.spinNs);
         if (loOwned) flushPlane(ex, nullptr, lo0, segP, pfLo);
         if (hiOwned) flushPlane(ex + 1, segM, nullptr, nullptr, nullptr);
         if (ex == exEnd && xb == NX) flushPlane(NX - 1, nullptr, hi0, nullptr, pfHi);  // last node plane: nothing above it
@@ -677,6 +679,9 @@ struct SweepPlan {
             const double cost = rounds * (double)(len + 1);
             if (cost < bestCost) { bestCost = cost; best = c; }
         }
+        if (const char* ev = getenv("EWB_CHUNKS")) best = std::max(1, atoi(ev));
+        a.spinNs = 0;
+        if (const char* ev = getenv("EWB_SPIN_NS")) a.spinNs = atoi(ev);
         a.chunkLen = (int)((nX + 1 + best - 1) / best);
         a.nChunks = (int)((nX + 1 + a.chunkLen - 1) / a.chunkLen);
         a.coords = b->coords; a.U = b->U; a.dU = b->dU; a.stateRef = b->state_ref; a.stateTemp = b->state_temp;

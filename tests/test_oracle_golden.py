@@ -58,3 +58,30 @@ def test_von_mises_newton_failure_flag():
     de[..., 3] = 0.5
     s, C, k, failed = port.von_mises(props, stress, de, np.zeros((1, 1)))
     assert failed.shape == (1, 1)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_c_oracle_matches_reference_golden(name):
+    """oracle/element_loop.c (the OpenMP CPU baseline) against the reference's golden vectors."""
+    import subprocess
+
+    from conftest import ROOT
+
+    subprocess.check_call(["make", "-s", "-C", ROOT + "/oracle"])
+    from oracle import cport
+
+    c = cport.load()
+    g = load_golden(name)
+    for p in range(int(g["nPasses"])):
+        o = c.assemble(str(g["elType"]), str(g["material"]), g["props"], g["coords"], g["conn"], g[f"U{p}"], g[f"dU{p}"], g[f"stateRef{p}"])
+        assert np.array_equal(o["indptr"], g["indptr"]) and np.array_equal(o["indices"], g["indices"])
+        for key in ("data", "P", "F", "stateTemp"):
+            assert relerr(o[key], g[f"{key}{p}"]) < TOL, key
+        if f"V{p}" in g:
+            assert relerr(o["V"], g[f"V{p}"]) < TOL
+            # the reference's sequential updateCSR order is reproduced bit for bit on the reference's own V
+            data = np.empty(g["indices"].size)
+            x = np.ascontiguousarray(o["x"], dtype=np.int32)
+            V = np.ascontiguousarray(g[f"V{p}"])
+            c.lib.ewo_update_csr(x.size, x.ctypes.data, V.ctypes.data, data.ctypes.data, data.size)
+            assert np.array_equal(data, g[f"data{p}"])
