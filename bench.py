@@ -157,7 +157,8 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from edelweissfe_b200 import ElementAssembly, _lib, box_mesh
+    from edelweissfe_b200 import _lib
+    from edelweissfe_b200.partition import SlabAssembly
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -165,10 +166,19 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- the rank's slab of the (n[0]*world) x n[1] x n[2] BoxGen box -------------------------
+    # (contiguous element-plane blocks, each GPU owning its CSR rows; interface rows exchanged over NCCL)
     l = (float(n[0]), float(n[1]), float(n[2]))
-    coords, conn = box_mesh(n[0], n[1], n[2], lX=l[0], lY=l[1], lZ=l[2], x0=rank * l[0], elType=elType)
-    asm = ElementAssembly(elType, conn, coords, material, props, device=dev, box=n if "20" not in elType else None)
-    del conn
+    if "20" in elType:
+        from edelweissfe_b200 import ElementAssembly, box_mesh
+
+        assert world == 1, "C3D20 runs on the generic path, single GPU"
+        coords, conn = box_mesh(n[0], n[1], n[2], lX=l[0], lY=l[1], lZ=l[2], elType=elType)
+        asm = ElementAssembly(elType, conn, coords, material, props, device=dev)
+        slab = None
+    else:
+        slab = SlabAssembly((n[0] * world, n[1], n[2]), (l[0] * world, l[1], l[2]), elType, material, props, rank, world, dev)
+        asm = slab.asm
+    coords = asm.coords.cpu().numpy()
     dU = make_inputs(recipe, coords, n, l, seed=rank)
     hU = torch.from_numpy(dU.copy()).pin_memory()
     hdU = torch.from_numpy(dU.copy()).pin_memory()
@@ -178,7 +188,10 @@ def main():
     indptr, indices = asm.csr_pattern()
 
     def step():
-        asm.assemble(flags)
+        if slab is not None:
+            slab.assemble(flags)
+        else:
+            asm.assemble(flags)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -220,7 +233,7 @@ def main():
         def e2e_step():
             asm.U.copy_(hU, non_blocking=True)
             asm.dU.copy_(hdU, non_blocking=True)
-            asm.assemble(flags)
+            step()
             hP.copy_(asm.P, non_blocking=True)
             hF.copy_(asm.F, non_blocking=True)
             hK.copy_(asm.csr_data, non_blocking=True)
@@ -250,12 +263,14 @@ def main():
     peak, peak_src = hbm_peak()
     balg = algorithmic_bytes_per_element(asm.nn, asm.nGp, asm.nState, asm.nnz, asm.nEl, asm.nNode)
     achieved = balg * asm.nEl / (ms_per_step * 1e-3) / 1e9  # GB/s per GPU (per-rank launch)
-    fused = bool(asm.lib.ewb_plan_is_box(asm.plan)) and not args.generic
+    fused = bool(asm.lib.ewb_plan_is_box(asm.plan)) and not args.generic and "20" not in elType
     line = {
         "metric": "Hexa8 K+P assembly throughput", "value": value, "unit": "Melem/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "elements_per_gpu": asm.nEl, "box_per_gpu": list(n), "nnz_per_gpu": asm.nnz, "dofs_per_gpu": asm.nDof,
-                   "path": "fused-sweep" if fused else "generic-two-phase", "l2": "inputs+outputs (>3.6 GB/step) larger than the 126 MB L2"},
+                   "path": "fused-sweep" if fused else "generic-two-phase", "l2": "inputs+outputs (>3.6 GB/step) larger than the 126 MB L2",
+                   "partition": "x-slabs of %d element planes per GPU, ghost-plane rows sent to the upper neighbour (NCCL P2P), %d B per interface"
+                                % (n[0], slab.interface_bytes if slab is not None else 0) if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_element": balg,
                      "kernel": "sweepKernel (1 launch = 1 step)" if fused else "computeElementsVij+gatherResidual+updateCsr (3 launches = 1 step)"},

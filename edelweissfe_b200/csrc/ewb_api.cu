@@ -274,6 +274,20 @@ __global__ void stateTransposeKernel(const double* __restrict__ src, double* __r
     }
 }
 
+// one warp per CSR row of the receiver's first node plane
+__global__ void interfaceAddKernel(const int32_t* __restrict__ indptr, int64_t nRows, double* __restrict__ data, const double* __restrict__ recv,
+                                   double* __restrict__ P, double* __restrict__ F, const double* __restrict__ rP, const double* __restrict__ rF) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nRows) return;
+    const int64_t r0 = indptr[row], len = indptr[row + 1] - r0, half = len >> 1;
+    for (int64_t t = lane; t < half; t += 32) data[r0 + t] += recv[r0 + half + t];
+    if (lane == 0 && P != nullptr) {
+        P[row] += rP[row];
+        F[row] += rF[row];
+    }
+}
+
 __global__ void dirichletKernel(const int32_t* __restrict__ indptr3, const int64_t* __restrict__ adjPtr, const int32_t* __restrict__ adj,
                                 double* __restrict__ data, const int32_t* __restrict__ dofs, int64_t n) {
     (void)indptr3;
@@ -431,6 +445,16 @@ int ewb_state_to_aos(const double* soa, double* aos, int64_t nEl, int nGp, int n
     if (!aos || !soa) return fail(EWB_ERR_ARG, "null state buffer");
     const int64_t total = nEl * nGp * nState;
     stateTransposeKernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(soa, aos, nEl, nGp, nState, 0);
+    LAUNCH_CHECK();
+    return EWB_OK;
+}
+
+int ewb_interface_add(const int32_t* indptr_dev, int64_t n_rows, double* data, const double* recv, double* P, double* F, const double* rP,
+                      const double* rF, void* stream) {
+    if (!indptr_dev || !data || !recv || n_rows <= 0) return fail(EWB_ERR_ARG, "ewb_interface_add: bad arguments");
+    const int B = 256;
+    const int64_t threads = n_rows * 32;
+    interfaceAddKernel<<<(unsigned)((threads + B - 1) / B), B, 0, (cudaStream_t)stream>>>(indptr_dev, n_rows, data, recv, P, F, rP, rF);
     LAUNCH_CHECK();
     return EWB_OK;
 }

@@ -1,0 +1,146 @@
+"""Multi-GPU slab decomposition of a BoxGen box.
+
+BoxGen numbers elements and nodes ix-major (generators/boxgen.py:133-136,168-170), so contiguous
+element-plane ranges are slabs in x and every slab's nodes are a contiguous CSR row range.  Rank g owns
+element planes [a_g, a_g+1) and node planes [a_g, a_g+1) (the last rank also the final plane).  Its local
+mesh holds one more node plane — the ghost plane a_g+1 owned by rank g+1 — whose partial rows are the
+contiguous TAIL of the local CSR value array (and of P, F).  One neighbour exchange per assembly:
+
+    rank g  --(tail of csr_data, P, F)-->  rank g+1   (torch.distributed P2P: NCCL over NVLink on GPUs)
+
+then `ewb_interface_add` adds the dx=0 half of the received rows onto the receiver's first node plane
+(own contribution first, neighbour second: deterministic).  The dx=-1 half of the received rows is the
+receiver's lower halo block.  No all-reduce is needed for K.
+
+The reference has no multi-process mode; this layout is the B200-native extension of its prange over
+elements (solvers/nonlinearimplicitstaticparallelmk2.pyx:157-160).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+
+def slab_ranges(nX: int, world: int):
+    """Element-plane ranges [a_g, a_g+1) per rank, as even as possible."""
+    base, rem = divmod(nX, world)
+    out, a = [], 0
+    for g in range(world):
+        b = a + base + (1 if g < rem else 0)
+        out.append((a, b))
+        a = b
+    return out
+
+
+@dataclass
+class SlabLayout:
+    """Pure index logic of one rank's slab (shared by the CUDA path and the CPU tests)."""
+
+    nX: int
+    nY: int
+    nZ: int
+    rank: int
+    world: int
+
+    def __post_init__(self):
+        self.a, self.b = slab_ranges(self.nX, self.world)[self.rank]
+        self.nXloc = self.b - self.a
+        if self.nXloc < 1:
+            raise ValueError("every rank needs at least one element plane")
+        self.planeNodes = (self.nY + 1) * (self.nZ + 1)
+        self.planeDofs = 3 * self.planeNodes
+        self.nNodeLoc = (self.nXloc + 1) * self.planeNodes
+        self.nDofLoc = 3 * self.nNodeLoc
+        self.has_lower = self.rank > 0  # receives interface rows from rank-1
+        self.has_upper = self.rank < self.world - 1  # sends its ghost-plane rows to rank+1
+        # owned dofs: all local dofs except the ghost plane (kept by the last rank, which has none)
+        self.ownedDofs = self.nDofLoc - (self.planeDofs if self.has_upper else 0)
+
+    def node_offset(self):
+        """global node index = local node index + node_offset()."""
+        return self.a * self.planeNodes
+
+    def tail_start(self, indptr):
+        """First CSR slot of the ghost plane's rows (the tail sent upwards)."""
+        return int(indptr[self.nDofLoc - self.planeDofs])
+
+    def head_nnz(self, indptr):
+        """Number of CSR slots of the first node plane's rows (size of the message received from below)."""
+        return int(indptr[self.planeDofs])
+
+    def local_mesh(self, lX, lY, lZ, elType="C3D8", x0=0.0, y0=0.0, z0=0.0):
+        from .boxgen import box_mesh
+
+        h = lX / self.nX
+        return box_mesh(self.nXloc, self.nY, self.nZ, lX=h * self.nXloc, lY=lY, lZ=lZ, x0=x0 + h * self.a, y0=y0, z0=z0, elType=elType)
+
+
+def exchange_tails(layout: SlabLayout, data, P, F, recv, recvP, recvF, indptr_host, dist, group=None):
+    """Send this rank's ghost-plane tail upwards, receive the lower neighbour's tail (blocking P2P batch)."""
+    ops = []
+    if layout.has_upper:
+        ts = layout.tail_start(indptr_host)
+        d0 = layout.nDofLoc - layout.planeDofs
+        ops += [dist.P2POp(dist.isend, data[ts:], layout.rank + 1, group), dist.P2POp(dist.isend, P[d0:], layout.rank + 1, group),
+                dist.P2POp(dist.isend, F[d0:], layout.rank + 1, group)]
+    if layout.has_lower:
+        ops += [dist.P2POp(dist.irecv, recv, layout.rank - 1, group), dist.P2POp(dist.irecv, recvP, layout.rank - 1, group),
+                dist.P2POp(dist.irecv, recvF, layout.rank - 1, group)]
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+
+
+class SlabAssembly:
+    """One rank's share of a distributed BoxGen assembly: local ElementAssembly + interface exchange."""
+
+    def __init__(self, n, lengths, elType, material, props, rank, world, device):
+        import torch
+
+        from .assembly import ElementAssembly
+
+        self.layout = SlabLayout(n[0], n[1], n[2], rank, world)
+        coords, conn = self.layout.local_mesh(*lengths, elType=elType)
+        self.asm = ElementAssembly(elType, conn, coords, material, props, device=device, box=(self.layout.nXloc, n[1], n[2]))
+        self.indptr, self.indices = self.asm.csr_pattern()
+        self.indptr_host = self.indptr.cpu().numpy()
+        lay = self.layout
+        f64 = dict(dtype=torch.float64, device=self.asm.device)
+        head = lay.head_nnz(self.indptr_host)
+        self.recv = torch.zeros(head if lay.has_lower else 1, **f64)
+        self.recvP = torch.zeros(lay.planeDofs if lay.has_lower else 1, **f64)
+        self.recvF = torch.zeros(lay.planeDofs if lay.has_lower else 1, **f64)
+        self.interface_bytes = 8 * (head + 2 * lay.planeDofs) if lay.has_lower else 0
+
+    def assemble(self, flags=0, group=None):
+        """Local fused assembly, then the neighbour exchange and the interface add (all on the current stream)."""
+        import torch.distributed as dist
+
+        from ._lib import check
+
+        a, lay = self.asm, self.layout
+        a.assemble(flags)
+        if lay.world > 1:
+            exchange_tails(lay, a.csr_data, a.P, a.F, self.recv, self.recvP, self.recvF, self.indptr_host, dist, group)
+            if lay.has_lower:
+                p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+                check(a.lib.ewb_interface_add(p(self.indptr), lay.planeDofs, p(a.csr_data), p(self.recv), p(a.P), p(a.F), p(self.recvP), p(self.recvF),
+                                              a._stream()))
+
+    # owned part of the distributed system (rows of owned dofs, local column numbering + lower halo block in self.recv)
+    def owned_slices(self):
+        lay = self.layout
+        nnz_owned = int(self.indptr_host[lay.ownedDofs])
+        return slice(0, lay.ownedDofs), slice(0, nnz_owned)
+
+
+def interface_add_host(indptr, n_rows, data, recv, P, F, rP, rF):
+    """NumPy mirror of ewb_interface_add (host-side index logic; used by the CPU gloo tests)."""
+    for row in range(n_rows):
+        r0, r1 = int(indptr[row]), int(indptr[row + 1])
+        half = (r1 - r0) // 2
+        data[r0 : r0 + half] += recv[r0 + half : r1]
+    P[:n_rows] += rP
+    F[:n_rows] += rF

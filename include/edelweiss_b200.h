@@ -120,6 +120,17 @@ int ewb_state_to_aos(const double* soa_dev, double* aos_dev, int64_t n_el, int n
  * zero the CSR rows of the given dofs and put 1 on their diagonal (pattern unchanged). */
 int ewb_apply_dirichlet_k(const ewb_plan* plan, double* csr_data_dev, const int32_t* dofs_dev, int64_t n, void* stream);
 
+/* ---- multi-GPU slab interface --------------------------------------------------------
+ * Rank g owns the node planes [a_g, a_g+1) of a BoxGen box split along x; its local mesh also holds
+ * the ghost plane a_g+1, whose partial CSR rows / P / F (contiguous tail of the local arrays) are sent
+ * to rank g+1.  On the receiver the first node plane has rows of the same lengths, laid out
+ * [dx=0 | dx=+1] where the sender has [dx=-1 | dx=0]: this adds the neighbour's dx=0 half onto the
+ * local rows (own contribution first, neighbour second: fixed order).  The dx=-1 half stays in `recv`
+ * and is the rank's lower halo block (columns = nodes of the neighbour's last owned plane).
+ * indptr_dev: local CSR indptr; n_rows = 3 * nodes per plane. */
+int ewb_interface_add(const int32_t* indptr_dev, int64_t n_rows, double* csr_data_dev, const double* recv_rows_dev, double* P_dev,
+                      double* F_dev, const double* recv_P_dev, const double* recv_F_dev, void* stream);
+
 /* number of this library's kernel launches since load (bench.py's gpu_launches) */
 int64_t ewb_launch_count(void);
 
