@@ -155,6 +155,49 @@ class ElementAssembly:
         dst = self.state_temp if which == "temp" else self.state_ref
         check(self.lib.ewb_state_to_soa(_ptr(a), _ptr(dst), self.nEl, self.nGp, self.nState, self._stream()))
 
+    # ---- host-facing calls (what the solver plugin uses) -----------------------------------------
+    def _pinned(self, name, n):
+        buf = getattr(self, "_pin_" + name, None)
+        if buf is None or buf.numel() != n:
+            buf = torch.empty(n, dtype=torch.float64).pin_memory()
+            setattr(self, "_pin_" + name, buf)
+        return buf
+
+    def compute_host(self, U, dU, stateRef_aos, stateTemp_aos, time=(0.0, 0.0), dT=0.0, flags=0):
+        """computeElements with HOST arrays: U, dU [nDof], stateRef [nEl,nGp,nState] in; returns (P, F) and
+        fills stateTemp_aos in place.  K stays on the device until csr_data_host().  Raises CutbackRequest."""
+        hU, hdU = self._pinned("U", self.nDof), self._pinned("dU", self.nDof)
+        hU.numpy()[:] = U
+        hdU.numpy()[:] = dU
+        hS = self._pinned("S", self.nEl * self.nGp * self.nState)
+        hS.numpy()[:] = np.asarray(stateRef_aos).reshape(-1)
+        self.U.copy_(hU, non_blocking=True)
+        self.dU.copy_(hdU, non_blocking=True)
+        scratch = getattr(self, "_aos_scratch", None)
+        if scratch is None:
+            scratch = self._aos_scratch = torch.empty(self.nEl * self.nGp * self.nState, dtype=torch.float64, device=self.device)
+        scratch.copy_(hS, non_blocking=True)
+        check(self.lib.ewb_state_to_soa(_ptr(scratch), _ptr(self.state_ref), self.nEl, self.nGp, self.nState, self._stream()))
+        self.assemble(flags, time=time, dT=dT)
+        check(self.lib.ewb_state_to_aos(_ptr(self.state_temp), _ptr(scratch), self.nEl, self.nGp, self.nState, self._stream()))
+        hP, hF = self._pinned("P", self.nDof), self._pinned("F", self.nDof)
+        hP.copy_(self.P, non_blocking=True)
+        hF.copy_(self.F, non_blocking=True)
+        hS.copy_(scratch, non_blocking=True)
+        self.poll()
+        np.asarray(stateTemp_aos).reshape(-1)[:] = hS.numpy()
+        return hP.numpy().copy(), hF.numpy().copy()
+
+    def csr_pattern_host(self):
+        indptr, indices = self.csr_pattern()
+        return indptr.cpu().numpy(), indices.cpu().numpy()
+
+    def csr_data_host(self):
+        hK = self._pinned("K", self.nnz)
+        hK.copy_(self.csr_data, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return hK.numpy()
+
     # ---- host round trips -----------------------------------------------------------------------
     def to_scipy(self):
         import scipy.sparse as sp

@@ -1,0 +1,157 @@
+"""Host-side logic of the NISTB200 solver plugin, run on CPU against the UNMODIFIED reference
+(build container only: skipped when /root/reference is absent, e.g. on the GPU box).
+
+The CUDA backend is replaced by an oracle-backed stand-in with the same three host-facing methods, so
+these tests cover: registration through config/solvers.py, extraction of connectivity / material /
+state from the reference's objects, state views (acceptLastState, field outputs), merging into the
+reference's CSR pattern — on the reference's own regression jobs and their U.ref golden vectors."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+sys.path.insert(0, ROOT)
+from tools import refshim  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not refshim.reference_available(), reason="reference tree not present")
+
+
+class OracleBackend:
+    """Test double for edelweissfe_b200.ElementAssembly (CPU, oracle arithmetic)."""
+
+    def __init__(self, elType, conn, coords, material, props, box=None):
+        from oracle import port
+
+        self.port = port
+        self.args = (elType, material, props, coords, conn)
+        self.box = box
+        self.out = None
+
+    def compute_host(self, U, dU, stateRef, stateTemp, time=(0, 0), dT=0.0, flags=0):
+        from edelweissfe_b200.assembly import CutbackRequest
+
+        elType, material, props, coords, conn = self.args
+        o = self.port.assemble(elType, material, props, coords, conn, np.array(U), np.array(dU), np.array(stateRef), want_vij=False)
+        if o["failed"].any():
+            raise CutbackRequest("Von Mises Newton failed.", 0.5)
+        stateTemp[...] = o["stateTemp"]
+        self.out = o
+        return o["P"], o["F"]
+
+    def csr_pattern_host(self):
+        return self.out["indptr"], self.out["indices"]
+
+    def csr_data_host(self):
+        return self.out["data"]
+
+
+def _run_job(testdir, solver="NISTB200", inp="test.inp", backend=OracleBackend):
+    refshim.bootstrap()
+    refshim.build_native_helpers()
+    from edelweissfe.drivers.inputfiledrivensimulation import finiteElementSimulation
+    from edelweissfe.utils.inputfileparser import parseInputFile
+
+    from edelweissfe_b200 import nistb200
+
+    created = []
+
+    def factory(*a, **k):
+        b = backend(*a, **k)
+        created.append(b)
+        return b
+
+    nistb200.register(factory)
+    cwd = os.getcwd()
+    os.chdir(os.path.join(refshim.REFERENCE_ROOT, "testfiles", testdir))
+    try:
+        text = open(inp).read()
+        if solver != "NIST":
+            text = text.replace("solver=NIST,", f"solver={solver},")
+        tmp = f"/tmp/ewb_{testdir}_{solver}.inp"
+        open(tmp, "w").write(text)
+        # outputs (ensight files) go to a scratch dir
+        os.chdir("/tmp")
+        inputFile = parseInputFile(tmp)
+        inputFile["*output"] = [o for o in inputFile["*output"] if o.get("type") != "ensight"]
+        model, _foc = finiteElementSimulation(inputFile, verbose=False, suppressPlots=True)
+    finally:
+        os.chdir(cwd)
+    U = np.hstack([f["U"].flatten() for f in model.nodeFields.values()] + [v.value for v in model.scalarVariables.values()])
+    return U, model, created
+
+
+@pytest.mark.parametrize("testdir", ["WallShearHexa8", "TensionBarHexa8", "CantileverBeamHexa8", "WallShearHexa20"])
+def test_reference_jobs_through_plugin(testdir):
+    U, model, created = _run_job(testdir)
+    Uref = np.loadtxt(os.path.join(refshim.REFERENCE_ROOT, "testfiles", testdir, "U.ref"))
+    assert created, "the plugin's computeElements was not used"
+    # the reference's own acceptance test: max-abs < 1e-6 (_cli/_run_tests_edelweissfe.py:102-105)
+    assert np.abs(U - Uref).max() < 1e-6
+    # and tighter against the reference's own serial solver on the same machine (what remains is the
+    # round-off of K amplified by the conditioning of these thin-plate / beam problems in SuperLU)
+    U0, _, _ = _run_job(testdir, solver="NIST")
+    assert np.abs(U - U0).max() < 1e-8
+
+
+def test_box_detection_and_state_views():
+    U, model, created = _run_job("WallShearHexa8")
+    assert created[0].box == (20, 20, 2)
+    el = next(iter(model.elements.values()))
+    # getResultArray keeps returning live views of the accepted state (element.py:386-409)
+    s = el.getResultArray("stress", 0)
+    assert s.base is not None and np.abs(s).max() > 0
+
+
+def test_von_mises_job_matches_reference_solver():
+    """3-D von Mises job shipped without U.ref (testfiles/WallShearHexa8VonMises): plugin vs the reference's NIST."""
+    import re
+
+    refshim.bootstrap()
+    src = open(os.path.join(refshim.REFERENCE_ROOT, "testfiles", "WallShearHexa8VonMises", "testLong.inp")).read()
+    # shrink the mesh so that the job takes seconds
+    src = re.sub(r"nX\s*=\s*\d+", "nX=4", src)
+    src = re.sub(r"nY\s*=\s*\d+", "nY=4", src)
+    open("/tmp/ewb_vm_small.inp", "w").write(src)
+    os.makedirs("/tmp/ewb_vm", exist_ok=True)
+    res = {}
+    for solver in ("NIST", "NISTB200"):
+        d = os.path.join(refshim.REFERENCE_ROOT, "testfiles", "WallShearHexa8VonMises")
+        U, model, created = _run_job_path("/tmp/ewb_vm_small.inp", solver)
+        res[solver] = U
+    # load-controlled plasticity close to the limit load: both runs stop at the same Newton tolerances
+    # (config/phenomena.py:59-93), so they agree to that level (measured 1.3e-6 relative), not to round-off
+    assert np.abs(res["NIST"] - res["NISTB200"]).max() < 1e-5 * np.abs(res["NIST"]).max()
+
+
+def _run_job_path(path, solver):
+    refshim.bootstrap()
+    refshim.build_native_helpers()
+    from edelweissfe.drivers.inputfiledrivensimulation import finiteElementSimulation
+    from edelweissfe.utils.inputfileparser import parseInputFile
+
+    from edelweissfe_b200 import nistb200
+
+    created = []
+
+    def factory(*a, **k):
+        b = OracleBackend(*a, **k)
+        created.append(b)
+        return b
+
+    nistb200.register(factory)
+    text = open(path).read().replace("solver=NIST,", f"solver={solver},")
+    tmp = path + "." + solver
+    open(tmp, "w").write(text)
+    cwd = os.getcwd()
+    os.chdir("/tmp")
+    try:
+        inputFile = parseInputFile(tmp)
+        inputFile["*output"] = [o for o in inputFile["*output"] if o.get("type") != "ensight"]
+        model, _foc = finiteElementSimulation(inputFile, verbose=False, suppressPlots=True)
+    finally:
+        os.chdir(cwd)
+    U = np.hstack([f["U"].flatten() for f in model.nodeFields.values()] + [v.value for v in model.scalarVariables.values()])
+    return U, model, created

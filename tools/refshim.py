@@ -130,3 +130,10 @@ def build_cython_module(relpath: str, modname: str, openmp: bool = False):
 def csr_generator_class():
     bootstrap()
     return build_cython_module("edelweissfe/numerics/csrgenerator.pyx", "edelweissfe.numerics.csrgenerator").CSRGenerator
+
+
+def build_native_helpers():
+    """The two dependency-free Cython modules full jobs need."""
+    bootstrap()
+    build_cython_module("edelweissfe/numerics/csrgenerator.pyx", "edelweissfe.numerics.csrgenerator")
+    build_cython_module("edelweissfe/utils/elementresultcollector.pyx", "edelweissfe.utils.elementresultcollector")
