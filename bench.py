@@ -41,6 +41,14 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(workload, path):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(f"{workload}:{path}")
+    return None
+
+
 def algorithmic_bytes_per_element(nn, nGp, nState, nnz, nEl, nNode):
     """conn + coords + U,dU + state in/out + CSR values + P,F."""
     rho = nNode / nEl
@@ -120,7 +128,7 @@ def cpu_reference_leg(wl, sample_n, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="boxgen100_c3d8_linearelastic", choices=sorted(WORKLOADS))
@@ -271,7 +279,7 @@ def main():
                    "path": "fused-sweep" if fused else "generic-two-phase", "l2": "inputs+outputs (>3.6 GB/step) larger than the 126 MB L2",
                    "partition": "x-slabs of %d element planes per GPU, ghost-plane rows sent to the upper neighbour (NCCL P2P), %d B per interface"
                                 % (n[0], slab.interface_bytes if slab is not None else 0) if world > 1 else "single GPU"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.workload, "fused-sweep" if fused else "generic-two-phase"),
                      "peak_source": peak_src, "algorithmic_bytes_per_element": balg,
                      "kernel": "sweepKernel (1 launch = 1 step)" if fused else "computeElementsVij+gatherResidual+updateCsr (3 launches = 1 step)"},
         "clocks": clocks.summary(),
