@@ -433,6 +433,17 @@ int ewb_poll_status(ewb_plan* p, void* stream, double* pNewDT) {
     return EWB_OK;
 }
 
+#ifdef EWB_TIMING
+/* debug builds only: per-warp phase cycle counters of the last sweep launch, [nCTA][NW][8] */
+int64_t ewb_debug_timing(ewb_plan* p, long long* out_host, int64_t n) {
+    if (!p || !p->sweep.timingBuf) return -1;
+    const int64_t m = std::min<int64_t>(n, (int64_t)p->sweep.timingCount);
+    cudaDeviceSynchronize();
+    cudaMemcpy(out_host, p->sweep.timingBuf, m * sizeof(long long), cudaMemcpyDeviceToHost);
+    return m;
+}
+#endif
+
 int ewb_state_to_soa(const double* aos, double* soa, int64_t nEl, int nGp, int nState, void* stream) {
     if (!aos || !soa) return fail(EWB_ERR_ARG, "null state buffer");
     const int64_t total = nEl * nGp * nState;

@@ -42,7 +42,16 @@ struct SweepArgs {
     int wantK;
     int accumulatePF;
     int spinNs;  // back-off of the flag polling loops (tuning knob, EWB_SPIN_NS)
+    long long* timing;  // optional [gridDim][NW][8] cycle counters (EWB_TIMING builds only)
 };
+
+#ifdef EWB_TIMING
+#define EWB_TIC(t) const long long t = clock64()
+#define EWB_ACC(slot, t0) tacc[slot] += clock64() - (t0)
+#else
+#define EWB_TIC(t)
+#define EWB_ACC(slot, t0)
+#endif
 
 // Per-Gauss-point record published by phase A (doubles):
 //   LE: [0..8] J^-1 | [9] w detJ               | [10..15] -w detJ sigma
@@ -73,9 +82,10 @@ __device__ __forceinline__ int rowNode(int r) { return (0x76452310u >> (4 * r)) 
 // ---------------------------------------------------------------------------------------------
 // phase A: one lane = one Gauss point of one element
 // ---------------------------------------------------------------------------------------------
+// stg: the warp's staged nodal data [18 patch nodes][x,y,z,u0,u1,u2], already offset to this lane's element
+// (patch node of local node a = stg + (9 dx + 3 dy + dz) * 6).
 template <int MC, bool TL>
-__device__ __forceinline__ void gaussPointCompact(double* rec, const double* __restrict__ coords, const double* __restrict__ uSrc,
-                                                  const int (&nodeIdx)[8], int gp, const MatParams& mp,
+__device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg, int gp, const MatParams& mp,
                                                   const double* __restrict__ state_ref, double* __restrict__ state_temp, int64_t cstride,
                                                   bool writeState, int* failFlag) {
     using R = RecLayout<MC>;
@@ -93,10 +103,9 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* __r
         constexpr int a = decltype(ic)::value;
         double d[3];
         shapeDeriv<8, a>(xi, eta, zeta, d);
-        const double* xp = coords + 3 * nodeIdx[a];
-        const double* up = uSrc + 3 * nodeIdx[a];
-        const double x0 = __ldg(xp), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
-        const double u0 = __ldg(up), u1 = __ldg(up + 1), u2 = __ldg(up + 2);
+        constexpr int so = (((a >> 1) & 1) * 9 + ((a >> 2) & 1) * 3 + ((a ^ (a >> 1)) & 1)) * 6;
+        const double x0 = stg[so], x1 = stg[so + 1], x2 = stg[so + 2];
+        const double u0 = stg[so + 3], u1 = stg[so + 4], u2 = stg[so + 5];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             Jm[r * 3 + 0] = fma(d[r], x0, Jm[r * 3 + 0]);
@@ -417,6 +426,7 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
     volatile int* doneCnt = laneOff + NCOL * 32;  // [32] rounds completed per patch
     volatile int* flushedCnt = doneCnt + 32;      // [32] plane steps flushed per patch
     double* tables = smem + AL::TABLES;           // [NW][4][PER_EL]
+    double* stageAll = tables + (size_t)NW * 4 * R::PER_EL;  // [NW][108] nodal x,u of the warp's 3x3x2 patch nodes
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NX = A.nX + 1, NY = A.nY + 1, NZ = A.nZ + 1;
@@ -461,7 +471,6 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
     const int64_t cstride = (int64_t)A.nX * A.nY * A.nZ * 8;
     const double* __restrict__ uSrc = TL ? A.U : A.dU;
     const int64_t totYZ = (int64_t)totY * totZ;
-    const int strideX = NY * NZ;
 
     // this warp's patch and its dependencies
     const int p = warp, pyq = p / NPZ, pzq = p % NPZ;
@@ -568,22 +577,60 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
     const int aey = y0 - 1 + apy, aez = z0 - 1 + apz;
     const bool aValid = aey >= 0 && aey < A.nY && aez >= 0 && aez < A.nZ && apy <= ny && apz <= nz;
 
+    // cooperative, asynchronous staging of the patch's nodal coordinates / displacements for plane step `exs`
+    double* stage = stageAll + warp * 108;
+    const unsigned stageAddr = (unsigned)__cvta_generic_to_shared(stage);
+    auto stageLoad = [&](int exs) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int e = lane + 32 * it;
+            if (e < 108) {
+                const int sn = e / 6, c = e % 6;
+                const int X = sn / 9, Y = (sn / 3) % 3, Z = sn % 3;
+                const int iy = y0 - 1 + 2 * pyq + Y, iz = z0 - 1 + 2 * pzq + Z;
+                if (iy >= 0 && iy < NY && iz >= 0 && iz < NZ) {
+                    const int node = ((exs + X) * NY + iy) * NZ + iz;
+                    const double* src = (c < 3 ? A.coords : uSrc) + 3 * (int64_t)node + (c % 3);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(stageAddr + 8u * e), "l"(src) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // pull the Gauss-point state of plane step `exs` into L2 ahead of its use
+    auto statePrefetch = [&](int exs) {
+        if (aValid) {
+            const int64_t e = ((int64_t)exs * A.nY + aey) * A.nZ + aez;
+            const double* sp = A.stateRef + e * 8 + agp;
+#pragma unroll
+            for (int c = 0; c < 12 + (MC != MC_LE ? 1 : 0); ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + c * cstride));
+        }
+    };
+    stageLoad(exBegin);
+#ifdef EWB_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long tstart = clock64();
+#endif
     int step = 0;
     for (int ex = exBegin; ex <= exEnd; ++ex, ++step) {
+        EWB_TIC(tA);
         const bool loOwned = ex >= xa, hiOwned = (ex + 1) < xb;
         // ------------- phase A: the 4 elements of the patch -------------
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
         if (aValid) {
-            int nodeIdx[8];
-            const int n0 = (ex * NY + aey) * NZ + aez;
-#pragma unroll
-            for (int a = 0; a < 8; ++a) nodeIdx[a] = n0 + ndx(a) * strideX + ndy(a) * NZ + ndz(a);
             const int64_t e = ((int64_t)ex * A.nY + aey) * A.nZ + aez;
             const int64_t off = e * 8 + agp;
             const bool writeState = loOwned && apy >= 1 && apz >= 1;
-            gaussPointCompact<MC, TL>(wt + ak * R::PER_EL + agp * R::RS, A.coords, uSrc, nodeIdx, agp, A.mp, A.stateRef + off, A.stateTemp + off,
-                                      cstride, writeState, A.failFlag);
+            gaussPointCompact<MC, TL>(wt + ak * R::PER_EL + agp * R::RS, stage + ((ak >> 1) * 3 + (ak & 1)) * 6, agp, A.mp, A.stateRef + off,
+                                      A.stateTemp + off, cstride, writeState, A.failFlag);
         }
         __syncwarp();
+        if (ex < exEnd) {  // next plane's nodal data and state travel while this plane's stiffness blocks are computed
+            stageLoad(ex + 1);
+            statePrefetch(ex + 1);
+        }
+        EWB_ACC(0, tA);
         // per-step accumulation bases of this lane (segments rotate every plane)
         double* accBase[2];
 #pragma unroll
@@ -598,10 +645,15 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
             const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
             const bool valid = ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz;
             // ---- ordering: same-colour elements of different patches never share a node ----
+            EWB_TIC(tW);
             if (k == 0) waitFlags(flushedCnt, depF, hasF, step, A.failFlag, A.spinNs);
             waitFlags(doneCnt, depN, hasN, Rnd, A.failFlag, A.spinNs);
+            EWB_ACC(1, tW);
+            EWB_TIC(tB);
             double K0[9], K1[9], Pr[3];
             if (valid) elementBlocks<MC>(wt + k * R::PER_EL, lane, dNl, A.mp, A.wantK != 0, K0, K1, Pr);
+            EWB_ACC(2, tB);
+            EWB_TIC(tE);
             if (valid) {
                 const int ly = py - 1 + ndy(na), lz = pz - 1 + ndz(na);
                 if (planeOwned && ly >= 0 && ly < ny && lz >= 0 && lz < nz) {
@@ -630,26 +682,40 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
             __threadfence_block();
             __syncwarp();
             if (lane == 0) doneCnt[p] = Rnd + 1;
+            EWB_ACC(3, tE);
         }
         // ---------------- flush this warp's finished columns, rotate ----------------
+        EWB_TIC(tWF);
         waitFlags(doneCnt, depD, hasD, 4 * (step + 1), A.failFlag, A.spinNs);
+        EWB_ACC(4, tWF);
+        EWB_TIC(tF);
         if (loOwned) flushPlane(ex, nullptr, lo0, segP, pfLo);
         if (hiOwned) flushPlane(ex + 1, segM, nullptr, nullptr, nullptr);
         if (ex == exEnd && xb == NX) flushPlane(NX - 1, nullptr, hi0, nullptr, pfHi);  // last node plane: nothing above it
         __threadfence_block();
         __syncwarp();
         if (lane == 0) flushedCnt[p] = step + 1;
+        EWB_ACC(5, tF);
         {
             double* t0 = lo0; lo0 = hi0; hi0 = t0;
             double* t1 = pfLo; pfLo = pfHi; pfHi = t1;
         }
     }
+#ifdef EWB_TIMING
+    if (A.timing != nullptr && lane == 0) {
+        tacc[6] = clock64() - tstart;
+        tacc[7] = step;
+        for (int i = 0; i < 8; ++i) A.timing[((size_t)blockIdx.x * NW + warp) * 8 + i] = tacc[i];
+    }
+#endif
 }
 
 struct SweepPlan {
     int64_t nX = 0, nY = 0, nZ = 0;
     const int64_t* adjPtr = nullptr;  // unused by the kernel (closed-form row bases); kept for debugging
     int nSM = 148;
+    long long* timingBuf = nullptr;
+    size_t timingCount = 0;
 
     int build(int64_t nx, int64_t ny, int64_t nz) {
         nX = nx; nY = ny; nZ = nz;
@@ -664,6 +730,8 @@ struct SweepPlan {
     template <int MC, bool TL, int TY, int TZ>
     int launchT(const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st) {
         using Rec = RecLayout<MC>;
+        constexpr int NW_ = ((TY + 1) / 2) * ((TZ + 1) / 2);
+        (void)NW_;
         if ((nX + 1) * (nY + 1) * (nZ + 1) >= ((int64_t)1 << 31) / 3) return EWB_ERR_UNSUPPORTED;  // int32 node indexing inside the kernel
         SweepArgs a;
         a.nX = (int)nX; a.nY = (int)nY; a.nZ = (int)nZ;
@@ -681,6 +749,17 @@ struct SweepPlan {
         }
         if (const char* ev = getenv("EWB_CHUNKS")) best = std::max(1, atoi(ev));
         a.spinNs = 0;
+        a.timing = nullptr;
+#ifdef EWB_TIMING
+        {
+            static long long* tbuf = nullptr;
+            const size_t nT = (size_t)tiles * 64 * NW_ * 8;
+            if (!tbuf) cudaMalloc((void**)&tbuf, nT * sizeof(long long));
+            cudaMemsetAsync(tbuf, 0, nT * sizeof(long long), st);
+            a.timing = tbuf;
+            timingBuf = tbuf; timingCount = nT;
+        }
+#endif
         if (const char* ev = getenv("EWB_SPIN_NS")) a.spinNs = atoi(ev);
         a.chunkLen = (int)((nX + 1 + best - 1) / best);
         a.nChunks = (int)((nX + 1 + a.chunkLen - 1) / a.chunkLen);
@@ -690,7 +769,7 @@ struct SweepPlan {
         a.accumulatePF = (flags & EWB_FLAG_ACCUMULATE_PF) ? 1 : 0;
         constexpr int NW = ((TY + 1) / 2) * ((TZ + 1) / 2);
         auto kern = sweepKernel<MC, TL, TY, TZ>;
-        const size_t smem = ((size_t)AccLayout<TY, TZ>::TABLES + (size_t)NW * 4 * Rec::PER_EL) * sizeof(double);
+        const size_t smem = ((size_t)AccLayout<TY, TZ>::TABLES + (size_t)NW * 4 * Rec::PER_EL + (size_t)NW * 108) * sizeof(double);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EWB_ERR_CUDA;
         const int64_t grid = tiles * a.nChunks;
         kern<<<(unsigned)grid, NW * 32, smem, st>>>(a);

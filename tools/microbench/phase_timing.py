@@ -1,0 +1,40 @@
+"""Per-warp phase timing of the sweep kernel (debug build with -DEWB_TIMING, tools/microbench/libewb_timing.so)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from edelweissfe_b200 import _lib  # noqa: E402
+
+_lib.LIB_PATH = os.path.join(ROOT, "tools", "microbench", "libewb_timing.so")
+import torch  # noqa: E402
+
+from edelweissfe_b200 import ElementAssembly, box_mesh  # noqa: E402
+
+n = (100, 100, 100)
+coords, conn = box_mesh(*n, lX=100.0, lY=100.0, lZ=100.0)
+asm = ElementAssembly("C3D8", conn, coords, "linearelastic", [2.1e4, 0.22], box=n)
+dU = 1e-3 * torch.randn(asm.nDof, dtype=torch.float64)
+asm.U.copy_(dU)
+asm.dU.copy_(dU)
+for _ in range(3):
+    asm.assemble()
+asm.poll()
+lib = asm.lib
+lib.ewb_debug_timing.restype = C.c_int64
+lib.ewb_debug_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+NW = 16
+buf = np.zeros(225 * 64 * NW * 8, dtype=np.int64)
+m = lib.ewb_debug_timing(asm.plan, buf.ctypes.data, buf.size)
+t = buf[:m].reshape(-1, NW, 8)
+t = t[t[:, 0, 7] > 0]
+names = ["phaseA", "wait_round", "elementBlocks", "emission", "wait_flush", "flush", "total", "steps"]
+print("CTAs", t.shape[0], "steps per CTA", np.unique(t[:, 0, 7]))
+full = t[t[:, :, 6].max(axis=1) > np.percentile(t[:, :, 6].max(axis=1), 50)]  # the heavier half: full tiles
+steps = full[:, :, 7].mean()
+print("cycles per plane step, mean over warps of full-tile CTAs:")
+for i, nme in enumerate(names[:7]):
+    print(f"  {nme:14s} {full[:, :, i].mean() / steps:10.0f}   (per-warp min {full[:, :, i].mean(axis=0).min() / steps:8.0f}  max {full[:, :, i].mean(axis=0).max() / steps:8.0f})")
