@@ -424,6 +424,7 @@ int ewb_poll_status(ewb_plan* p, void* stream, double* pNewDT) {
     CUDA_TRY(cudaMemcpyAsync(p->failHost, p->failFlag, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemsetAsync(p->failFlag, 0, sizeof(int), st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (*p->failHost & 4) return fail(EWB_ERR_CUDA, "internal error: sweep kernel flag wait timed out (ordering bug)");
     if (*p->failHost & 1) {
         if (pNewDT) *pNewDT = 0.5;
         g_err = "Von Mises Newton failed.";

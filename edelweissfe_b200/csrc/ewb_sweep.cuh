@@ -42,7 +42,7 @@ struct SweepArgs {
     int wantK;
     int accumulatePF;
     int spinNs;  // back-off of the flag polling loops (tuning knob, EWB_SPIN_NS)
-    long long* timing;  // optional [gridDim][NW][8] cycle counters (EWB_TIMING builds only)
+    long long* timing;  // optional [gridDim][NW][12] cycle counters (EWB_TIMING builds only)
 };
 
 #ifdef EWB_TIMING
@@ -87,7 +87,13 @@ __device__ __forceinline__ int rowNode(int r) { return (0x76452310u >> (4 * r)) 
 template <int MC, bool TL>
 __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg, int gp, const MatParams& mp,
                                                   const double* __restrict__ state_ref, double* __restrict__ state_temp, int64_t cstride,
-                                                  bool writeState, int* failFlag) {
+                                                  bool writeState, int* failFlag, long long* tsub = nullptr) {
+#ifdef EWB_TIMING
+    long long tq0 = clock64();
+#define EWB_SUB(i) do { const long long tq1 = clock64(); if (tsub) tsub[i] += tq1 - tq0; tq0 = tq1; } while (0)
+#else
+#define EWB_SUB(i)
+#endif
     using R = RecLayout<MC>;
     constexpr int NST = 12 + (MC != MC_LE ? 1 : 0);
     double st[13];
@@ -116,12 +122,14 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
             D[6 + r] = fma(u2, d[r], D[6 + r]);
         }
     });
+    EWB_SUB(0);
     const double detJ = det3(Jm);
     double iJ[9];
     inv3(Jm, detJ, iJ);
     const double wd = w * detJ;
 #pragma unroll
     for (int i = 0; i < 9; ++i) rec[i] = iJ[i];
+    EWB_SUB(1);
     // H[i][c] = du_i/dx_c = sum_r D[i][r] iJ[c][r]
     double H[9];
 #pragma unroll
@@ -192,10 +200,12 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
         st[11] = H[2] + H[6] + H[0] * H[2] + H[3] * H[5] + H[6] * H[8];
         st[12] = r.energy;
     }
+    EWB_SUB(2);
     if (writeState) {
 #pragma unroll
         for (int c = 0; c < NST; ++c) state_temp[c * cstride] = st[c];
     }
+    EWB_SUB(3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -385,6 +395,15 @@ struct AccLayout {
     static constexpr int TABLES = alignRes(INFO + (INFO_INTS + 1) / 2, 0);
 };
 
+// Ordering of shared-memory data against the shared-memory flags.  A warp's shared-memory accesses are performed in
+// program order, so a compiler barrier is enough; __threadfence_block() (MEMBAR.CTA) would also wait for every global
+// store in flight (state write-back, CSR flush) on every round.  -DEWB_STRICT_FENCE restores the full fence.
+#ifdef EWB_STRICT_FENCE
+#define EWB_SMEM_FENCE() __threadfence_block()
+#else
+#define EWB_SMEM_FENCE() asm volatile("" ::: "memory")
+#endif
+
 // Warp-level wait until flag[dep] >= target for up to 9 dependencies (lane i polls dependency i).
 // Bounded: a logic error sets bit 2 of the status word instead of hanging the GPU.
 __device__ __forceinline__ void waitFlags(const volatile int* flag, int dep, bool has, int target, int* failFlag, int spinNs) {
@@ -398,7 +417,7 @@ __device__ __forceinline__ void waitFlags(const volatile int* flag, int dep, boo
         }
         if (spinNs > 0) __nanosleep(spinNs);
     }
-    __threadfence_block();
+    EWB_SMEM_FENCE();
 }
 
 // One warp per 2x2 element patch; number of warps == number of patches of the tile.
@@ -412,6 +431,7 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
     constexpr int NT = NW * 32;
     static_assert((TY & 1) == 1 && (TZ & 1) == 1, "tile edge must be odd (2x2 element patches)");
     static_assert(NW <= 32, "at most 32 patches per tile");
+    constexpr bool COMPUTE_FIRST = NW <= 12;  // >= 168 registers per thread available
 
     extern __shared__ double smem[];
     double* seg0a = smem + AL::OFF_0A;  // dx=0 segment, ping
@@ -525,17 +545,17 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
     // flush the finished segments (nullptr = not finished) of this warp's owned nodes of plane ix, clear them
     auto flushPlane = [&](int ix, double* sM, double* s0, double* sP, double* pf) {
         const int cx = (ix > 0) + 1 + (ix < NX - 1);
-        const int64_t xbase = 9 * (int64_t)pre(ix) * totYZ;
+        double* xbase = A.data + 9 * (int64_t)pre(ix) * totYZ;
         const int rx0 = ix > 0 ? 1 : 0;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-            const int ly = 2 * pyq + (cc >> 1), lz = 2 * pzq + (cc & 1);
-            if (ly >= TY || lz >= TZ) continue;
-            const int col = ly * TZ + lz;
+            const int ly_ = 2 * pyq + (cc >> 1), lz_ = 2 * pzq + (cc & 1);
+            if (ly_ >= TY || lz_ >= TZ) continue;
+            const int col = ly_ * TZ + lz_;
             const int cycz = colCycz[col];
             if (cycz == 0) continue;
             const int lo = laneOff[col * 32 + lane];
-            double* rowBase = A.data + (xbase + (int64_t)(9 * cx) * colPart[col] + lo);
+            double* rowBase = xbase + ((int64_t)(9 * cx) * colPart[col] + lo);
             const int rowStride = 3 * cx * cycz;
             if (A.wantK && lane < 27) {
 #pragma unroll
@@ -546,11 +566,14 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
                     const bool ok = ix + dx >= 0 && ix + dx < NX && lo >= 0;
                     double* src = seg + col * CS + lane;
                     double* dst = rowBase + 3 * ((dx + rx0) * cycz);
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const double v = src[i * 27];
-                        src[i * 27] = 0.0;
-                        if (ok) dst[i * rowStride] = v;
+                    const double v0 = src[0], v1 = src[27], v2 = src[54];
+                    src[0] = 0.0;
+                    src[27] = 0.0;
+                    src[54] = 0.0;
+                    if (ok) {
+                        dst[0] = v0;
+                        dst[rowStride] = v1;
+                        dst[2 * rowStride] = v2;
                     }
                 }
             }
@@ -558,6 +581,7 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
                 const double pv = pf[col * 6 + lane], fv = pf[col * 6 + 3 + lane];
                 pf[col * 6 + lane] = 0.0;
                 pf[col * 6 + 3 + lane] = 0.0;
+                const int ly = 2 * pyq + (cc >> 1), lz = 2 * pzq + (cc & 1);
                 const int64_t dof = 3 * ((((int64_t)ix * NY + (y0 + ly)) * NZ) + (z0 + lz)) + lane;
                 if (A.accumulatePF) {
                     A.P[dof] += pv;
@@ -580,19 +604,21 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
     // cooperative, asynchronous staging of the patch's nodal coordinates / displacements for plane step `exs`
     double* stage = stageAll + warp * 108;
     const unsigned stageAddr = (unsigned)__cvta_generic_to_shared(stage);
+    int stNode = -1;  // lane < 18 stages patch node `lane` (X = lane/9, Y = (lane/3)%3, Z = lane%3): node offset at plane 0
+    if (lane < 18) {
+        const int X = lane / 9, Y = (lane / 3) % 3, Z = lane % 3;
+        const int iy = y0 - 1 + 2 * pyq + Y, iz = z0 - 1 + 2 * pzq + Z;
+        if (iy >= 0 && iy < NY && iz >= 0 && iz < NZ) stNode = 3 * ((X * NY + iy) * NZ + iz);
+    }
+    const int planeStride3 = 3 * NY * NZ;
     auto stageLoad = [&](int exs) {
+        if (stNode >= 0) {
+            const int64_t o = (int64_t)exs * planeStride3 + stNode;
+            const unsigned dst = stageAddr + 48u * lane;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int e = lane + 32 * it;
-            if (e < 108) {
-                const int sn = e / 6, c = e % 6;
-                const int X = sn / 9, Y = (sn / 3) % 3, Z = sn % 3;
-                const int iy = y0 - 1 + 2 * pyq + Y, iz = z0 - 1 + 2 * pzq + Z;
-                if (iy >= 0 && iy < NY && iz >= 0 && iz < NZ) {
-                    const int node = ((exs + X) * NY + iy) * NZ + iz;
-                    const double* src = (c < 3 ? A.coords : uSrc) + 3 * (int64_t)node + (c % 3);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(stageAddr + 8u * e), "l"(src) : "memory");
-                }
+            for (int c = 0; c < 3; ++c) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * c), "l"(A.coords + o + c) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 24u + 8u * c), "l"(uSrc + o + c) : "memory");
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -606,31 +632,50 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
             for (int c = 0; c < 12 + (MC != MC_LE ? 1 : 0); ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + c * cstride));
         }
     };
-    stageLoad(exBegin);
+    // phase A of plane step `exs` for the 4 elements of this warp's patch (records are warp-private)
 #ifdef EWB_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tsubA[4] = {0, 0, 0, 0};
     const long long tstart = clock64();
 #endif
-    int step = 0;
-    for (int ex = exBegin; ex <= exEnd; ++ex, ++step) {
-        EWB_TIC(tA);
-        const bool loOwned = ex >= xa, hiOwned = (ex + 1) < xb;
-        // ------------- phase A: the 4 elements of the patch -------------
+    auto phaseA = [&](int exs) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         if (aValid) {
-            const int64_t e = ((int64_t)ex * A.nY + aey) * A.nZ + aez;
+            const int64_t e = ((int64_t)exs * A.nY + aey) * A.nZ + aez;
             const int64_t off = e * 8 + agp;
-            const bool writeState = loOwned && apy >= 1 && apz >= 1;
+            const bool writeState = exs >= xa && apy >= 1 && apz >= 1;
             gaussPointCompact<MC, TL>(wt + ak * R::PER_EL + agp * R::RS, stage + ((ak >> 1) * 3 + (ak & 1)) * 6, agp, A.mp, A.stateRef + off,
-                                      A.stateTemp + off, cstride, writeState, A.failFlag);
+                                      A.stateTemp + off, cstride, writeState, A.failFlag
+#ifdef EWB_TIMING
+                                      , tsubA
+#endif
+            );
         }
         __syncwarp();
+    };
+    stageLoad(exBegin);
+    phaseA(exBegin);
+
+    // per-round loop invariants: element validity (warp uniform), ownership of this lane's row node, tile-image offset
+    unsigned validMask = 0, ownMask = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int py = 2 * pyq + (k >> 1), pz = 2 * pzq + (k & 1);
+        const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
+        if (ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz) validMask |= 1u << k;
+        const int ly = py - 1 + ndy(na), lz = pz - 1 + ndz(na);
+        if (ly >= 0 && ly < ny && lz >= 0 && lz < nz) ownMask |= 1u << k;
+    }
+    const int eOff0 = (2 * pyq - 1) * TZ + (2 * pzq - 1);
+
+    int step = 0;
+    for (int ex = exBegin; ex <= exEnd; ++ex, ++step) {
+        const bool loOwned = ex >= xa, hiOwned = (ex + 1) < xb;
         if (ex < exEnd) {  // next plane's nodal data and state travel while this plane's stiffness blocks are computed
             stageLoad(ex + 1);
             statePrefetch(ex + 1);
         }
-        EWB_ACC(0, tA);
         // per-step accumulation bases of this lane (segments rotate every plane)
         double* accBase[2];
 #pragma unroll
@@ -641,23 +686,22 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
             const int Rnd = 4 * step + k;
-            const int py = 2 * pyq + (k >> 1), pz = 2 * pzq + (k & 1);
-            const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
-            const bool valid = ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz;
-            // ---- ordering: same-colour elements of different patches never share a node ----
+            const bool valid = (validMask >> k) & 1;
+            double K0[9], K1[9], Pr[3];
+            // ---- ordering: same-colour elements of different patches never share a node.  With registers to spare the
+            // blocks are computed BEFORE the wait, so a fast warp's tensor work overlaps its neighbours' accumulation. ----
+            EWB_TIC(tB);
+            if (COMPUTE_FIRST && valid) elementBlocks<MC>(wt + k * R::PER_EL, lane, dNl, A.mp, A.wantK != 0, K0, K1, Pr);
+            EWB_ACC(2, tB);
             EWB_TIC(tW);
             if (k == 0) waitFlags(flushedCnt, depF, hasF, step, A.failFlag, A.spinNs);
             waitFlags(doneCnt, depN, hasN, Rnd, A.failFlag, A.spinNs);
             EWB_ACC(1, tW);
-            EWB_TIC(tB);
-            double K0[9], K1[9], Pr[3];
-            if (valid) elementBlocks<MC>(wt + k * R::PER_EL, lane, dNl, A.mp, A.wantK != 0, K0, K1, Pr);
-            EWB_ACC(2, tB);
+            if (!COMPUTE_FIRST && valid) elementBlocks<MC>(wt + k * R::PER_EL, lane, dNl, A.mp, A.wantK != 0, K0, K1, Pr);
             EWB_TIC(tE);
             if (valid) {
-                const int ly = py - 1 + ndy(na), lz = pz - 1 + ndz(na);
-                if (planeOwned && ly >= 0 && ly < ny && lz >= 0 && lz < nz) {
-                    const int eOff = (py - 1) * TZ + (pz - 1);
+                if (planeOwned && ((ownMask >> k) & 1)) {
+                    const int eOff = eOff0 + (k >> 1) * TZ + (k & 1);
                     if (bq == 0) {
                         double* pf = pfBase + eOff * 6;
 #pragma unroll
@@ -679,11 +723,15 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
                     }
                 }
             }
-            __threadfence_block();
+            EWB_SMEM_FENCE();
             __syncwarp();
             if (lane == 0) doneCnt[p] = Rnd + 1;
             EWB_ACC(3, tE);
         }
+        // ------------- phase A of the NEXT plane: this warp's records are dead, nobody else reads them -------------
+        EWB_TIC(tA);
+        if (ex < exEnd) phaseA(ex + 1);
+        EWB_ACC(0, tA);
         // ---------------- flush this warp's finished columns, rotate ----------------
         EWB_TIC(tWF);
         waitFlags(doneCnt, depD, hasD, 4 * (step + 1), A.failFlag, A.spinNs);
@@ -692,7 +740,7 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
         if (loOwned) flushPlane(ex, nullptr, lo0, segP, pfLo);
         if (hiOwned) flushPlane(ex + 1, segM, nullptr, nullptr, nullptr);
         if (ex == exEnd && xb == NX) flushPlane(NX - 1, nullptr, hi0, nullptr, pfHi);  // last node plane: nothing above it
-        __threadfence_block();
+        EWB_SMEM_FENCE();
         __syncwarp();
         if (lane == 0) flushedCnt[p] = step + 1;
         EWB_ACC(5, tF);
@@ -705,7 +753,8 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
     if (A.timing != nullptr && lane == 0) {
         tacc[6] = clock64() - tstart;
         tacc[7] = step;
-        for (int i = 0; i < 8; ++i) A.timing[((size_t)blockIdx.x * NW + warp) * 8 + i] = tacc[i];
+        for (int i = 0; i < 8; ++i) A.timing[((size_t)blockIdx.x * NW + warp) * 12 + i] = tacc[i];
+        for (int i = 0; i < 4; ++i) A.timing[((size_t)blockIdx.x * NW + warp) * 12 + 8 + i] = tsubA[i];
     }
 #endif
 }
@@ -753,7 +802,7 @@ struct SweepPlan {
 #ifdef EWB_TIMING
         {
             static long long* tbuf = nullptr;
-            const size_t nT = (size_t)tiles * 64 * NW_ * 8;
+            const size_t nT = (size_t)tiles * 64 * NW_ * 12;
             if (!tbuf) cudaMalloc((void**)&tbuf, nT * sizeof(long long));
             cudaMemsetAsync(tbuf, 0, nT * sizeof(long long), st);
             a.timing = tbuf;
@@ -778,7 +827,15 @@ struct SweepPlan {
 
     int launch(int elType, int mc, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st, int* launches) {
         int rc = EWB_ERR_UNSUPPORTED;
-        if (elType == EWB_C3D8 && mc == MC_LE) rc = launchT<MC_LE, false, 7, 7>(mp, b, failFlag, flags, st);
+        const char* tileEnv = getenv("EWB_TILE");
+        const int tile = tileEnv ? atoi(tileEnv) : 75;
+        if (elType == EWB_C3D8 && mc == MC_LE) {
+            if (tile == 77) rc = launchT<MC_LE, false, 7, 7>(mp, b, failFlag, flags, st);
+            else if (tile == 55) rc = launchT<MC_LE, false, 5, 5>(mp, b, failFlag, flags, st);
+            else if (tile == 95) rc = launchT<MC_LE, false, 9, 5>(mp, b, failFlag, flags, st);
+            else if (tile == 57) rc = launchT<MC_LE, false, 5, 7>(mp, b, failFlag, flags, st);
+            else rc = launchT<MC_LE, false, 7, 5>(mp, b, failFlag, flags, st);
+        }
         else if (elType == EWB_C3D8 && mc == MC_VM) rc = launchT<MC_VM, false, 7, 5>(mp, b, failFlag, flags, st);
         else if (elType == EWB_C3D8TL && mc == MC_NH) rc = launchT<MC_NH, true, 7, 5>(mp, b, failFlag, flags, st);
         if (rc == EWB_OK) *launches = 1;

@@ -27,14 +27,14 @@ lib = asm.lib
 lib.ewb_debug_timing.restype = C.c_int64
 lib.ewb_debug_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
 NW = 16
-buf = np.zeros(225 * 64 * NW * 8, dtype=np.int64)
+buf = np.zeros(225 * 64 * NW * 12, dtype=np.int64)
 m = lib.ewb_debug_timing(asm.plan, buf.ctypes.data, buf.size)
-t = buf[:m].reshape(-1, NW, 8)
+t = buf[:m].reshape(-1, NW, 12)
 t = t[t[:, 0, 7] > 0]
-names = ["phaseA", "wait_round", "elementBlocks", "emission", "wait_flush", "flush", "total", "steps"]
+names = ["phaseA", "wait_round", "elementBlocks", "emission", "wait_flush", "flush", "total", "steps", "A:loads+J,D", "A:inverse+rec", "A:material", "A:state store"]
 print("CTAs", t.shape[0], "steps per CTA", np.unique(t[:, 0, 7]))
 full = t[t[:, :, 6].max(axis=1) > np.percentile(t[:, :, 6].max(axis=1), 50)]  # the heavier half: full tiles
 steps = full[:, :, 7].mean()
 print("cycles per plane step, mean over warps of full-tile CTAs:")
-for i, nme in enumerate(names[:7]):
+for i, nme in [(j, names[j]) for j in (0, 8, 9, 10, 11, 1, 2, 3, 4, 5, 6)]:
     print(f"  {nme:14s} {full[:, :, i].mean() / steps:10.0f}   (per-warp min {full[:, :, i].mean(axis=0).min() / steps:8.0f}  max {full[:, :, i].mean(axis=0).max() / steps:8.0f})")
