@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libedelweiss_b200.so")
+LIB_PATH = os.environ.get("EWB_LIB_PATH", os.path.join(_HERE, "libedelweiss_b200.so"))  # override: experiments only
 
 # enums of include/edelweiss_b200.h
 EWB_C3D8, EWB_C3D20, EWB_C3D8TL = 0, 1, 2

@@ -97,8 +97,13 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
     using R = RecLayout<MC>;
     constexpr int NST = 12 + (MC != MC_LE ? 1 : 0);
     double st[13];
+#ifdef EWB_EXP_NOSTATE
+#pragma unroll
+    for (int c = 0; c < NST; ++c) st[c] = 0.0;
+#else
 #pragma unroll
     for (int c = 0; c < NST; ++c) st[c] = state_ref[c * cstride];
+#endif
 
     double xi, eta, zeta, w;
     Gauss<8>::get(gp, xi, eta, zeta, w);
@@ -201,7 +206,11 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
         st[12] = r.energy;
     }
     EWB_SUB(2);
+#ifdef EWB_EXP_NOSTATE
+    if (writeState && st[0] == 123.456) {
+#else
     if (writeState) {
+#endif
 #pragma unroll
         for (int c = 0; c < NST; ++c) state_temp[c * cstride] = st[c];
     }
