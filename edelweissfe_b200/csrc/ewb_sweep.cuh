@@ -76,8 +76,8 @@ __device__ __forceinline__ int ndx(int a) { return (a >> 1) & 1; }
 __device__ __forceinline__ int ndy(int a) { return (a >> 2) & 1; }
 __device__ __forceinline__ int ndz(int a) { return (a ^ (a >> 1)) & 1; }
 
-// mma row/column r  <->  local node ROWPERM[r] = {0,1,3,2,5,4,6,7}[r]  (fewest bank conflicts, see AccLayout)
-__device__ __forceinline__ int rowNode(int r) { return (0x76452310u >> (4 * r)) & 7; }
+// mma row/column r  <->  local node ROWPERM[r] = {0,1,3,2,4,5,7,6}[r]  (conflict-free accumulation, see AccLayout)
+__device__ __forceinline__ int rowNode(int r) { return (0x67542310u >> (4 * r)) & 7; }
 
 // ---------------------------------------------------------------------------------------------
 // phase A: one lane = one Gauss point of one element
@@ -384,9 +384,10 @@ __device__ __forceinline__ void elementBlocks(const double* T, int lane, const d
 }
 
 // Accumulator geometry (doubles).  Per node column 81 doubles per segment, laid out [i][s9][j] so that a
-// CSR sub-row (27 values) is contiguous.  The four segment bases sit at residues 0,7,8,15 (mod 16 doubles)
-// and the mma rows are permuted (rowNode) — together the cheapest bank pattern found by exhaustive search
-// for the accumulation stores: 1.5 wavefronts per half-warp instead of 3.0.
+// CSR sub-row (27 values) is contiguous.  The four segment bases sit at residues 0,4,12,8 (mod 16 doubles)
+// and the mma rows are permuted (rowNode) — found by exhaustive search (tools/bank_search.py): every half-warp
+// of the accumulation loads/stores touches 16 different 8-byte banks, in both ping-pong roles of the dx=0
+// segments and for TZ = 5 and 7 (1.0 wavefront per half-warp; the naive layout needs 3.0).
 __host__ __device__ constexpr int alignRes(int x, int r) { return x + ((r - x % 16) + 16) % 16; }
 template <int TY, int TZ>
 struct AccLayout {
@@ -394,9 +395,9 @@ struct AccLayout {
     static constexpr int CS = 81;
     static constexpr int SEGSZ = NCOL * CS;
     static constexpr int OFF_0A = 0;
-    static constexpr int OFF_0B = alignRes(OFF_0A + SEGSZ, 7);
-    static constexpr int OFF_P = alignRes(OFF_0B + SEGSZ, 8);
-    static constexpr int OFF_M = alignRes(OFF_P + SEGSZ, 15);
+    static constexpr int OFF_0B = alignRes(OFF_0A + SEGSZ, 4);
+    static constexpr int OFF_P = alignRes(OFF_0B + SEGSZ, 12);
+    static constexpr int OFF_M = alignRes(OFF_P + SEGSZ, 8);
     static constexpr int ACC_END = OFF_M + SEGSZ;
     static constexpr int PF = ACC_END;               // [2][NCOL][6]
     static constexpr int INFO = PF + 12 * NCOL;      // int32: colPart[NCOL], colCycz[NCOL], laneOff[NCOL][32], done[32], flushed[32]
@@ -768,6 +769,370 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
 #endif
 }
 
+// Producer/consumer variant: NP consumer warps (one per 2x2 element patch: tensor-pipe stiffness blocks, shared-memory
+// accumulation, flush) + NWP producer warps that run phase A (kinematics, constitutive update, state write-back) one
+// plane step ahead into double-buffered Gauss-point records.  The latency-bound phase A thereby overlaps the FP64- and
+// shared-memory-bound consumer work instead of preceding it.
+template <int MC, bool TL, int TY, int TZ, int NWP>
+__global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 1) sweepKernelPC(const SweepArgs A) {
+    using R = RecLayout<MC>;
+    using AL = AccLayout<TY, TZ>;
+    constexpr int NPY = (TY + 1) / 2, NPZ = (TZ + 1) / 2, NW = NPY * NPZ;
+    constexpr int NCOL = TY * TZ;
+    constexpr int CS = AL::CS;
+    constexpr int NT = (NW + NWP) * 32;
+    static_assert((TY & 1) == 1 && (TZ & 1) == 1, "tile edge must be odd (2x2 element patches)");
+    static_assert(NW <= 32, "at most 32 patches per tile");
+    constexpr bool COMPUTE_FIRST = (NW + NWP) <= 12;
+
+    extern __shared__ double smem[];
+    double* seg0a = smem + AL::OFF_0A;  // dx=0 segment, ping
+    double* seg0b = smem + AL::OFF_0B;  // dx=0 segment, pong
+    double* segP = smem + AL::OFF_P;    // lower plane, dx=+1
+    double* segM = smem + AL::OFF_M;    // upper plane, dx=-1
+    double* pfA = smem + AL::PF;        // [NCOL][6] P,F of the lower plane
+    double* pfB = pfA + NCOL * 6;       // upper plane
+    int* colPart = reinterpret_cast<int*>(smem + AL::INFO);
+    int* colCycz = colPart + NCOL;
+    int* laneOff = colCycz + NCOL;                // [NCOL][32]
+    volatile int* doneCnt = laneOff + NCOL * 32;  // [32] rounds completed per patch
+    volatile int* flushedCnt = doneCnt + 32;      // [32] plane steps flushed per patch
+    double* tables = smem + AL::TABLES;           // [2][NW][4][PER_EL] double-buffered Gauss-point records
+    double* stageAll = tables + (size_t)2 * NW * 4 * R::PER_EL;  // [NWP][2][108] nodal x,u of a patch's 3x3x2 nodes
+    volatile int* producedCnt = reinterpret_cast<volatile int*>(stageAll + NWP * 216);  // [32] plane steps whose records are ready
+    volatile int* consumedCnt = producedCnt + 32;                                      // [32] plane steps whose records are consumed
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NX = A.nX + 1, NY = A.nY + 1, NZ = A.nZ + 1;
+
+    // work item -> (chunk, tile)
+    int item = blockIdx.x;
+    const int tz = item % A.tilesZ; item /= A.tilesZ;
+    const int ty = item % A.tilesY; item /= A.tilesY;
+    const int chunk = item;
+    const int y0 = ty * TY, z0 = tz * TZ;
+    const int ny = min(TY, NY - y0), nz = min(TZ, NZ - z0);  // owned node columns
+    const int xa = chunk * A.chunkLen, xb = min(xa + A.chunkLen, NX);
+    const int exBegin = max(xa - 1, 0), exEnd = min(xb - 1, A.nX - 1);
+
+    for (int i = tid; i < AL::INFO; i += NT) smem[i] = 0.0;
+    if (tid < 64) { doneCnt[tid] = 0; producedCnt[tid] = 0; }
+    // CSR row base of node (ix,iy,iz) in closed form: 9 * (sum of the degrees of all preceding nodes);
+    // deg = cx*cy*cz with c = 2 on a face, 3 inside (== the plan's node adjacency, checked by the parity tests).
+    // base = 9 * (pre(ix)*totY*totZ + cx * colPart),  colPart = pre(iy)*totZ + cy*pre(iz).
+    auto pre = [](int i) { return i == 0 ? 0 : 3 * i - 1; };
+    const int totY = 3 * NY - 2, totZ = 3 * NZ - 2;
+    for (int t = tid; t < NCOL * 32; t += NT) {
+        const int col = t >> 5, e = t & 31;
+        const int ly = col / TZ, lz = col % TZ;
+        const int iy = y0 + ly, iz = z0 + lz;
+        const bool colValid = ly < ny && lz < nz;
+        const int cy = (iy > 0) + 1 + (iy < NY - 1), cz = (iz > 0) + 1 + (iz < NZ - 1);
+        if (e == 0) {
+            colPart[col] = colValid ? pre(iy) * totZ + cy * pre(iz) : 0;
+            colCycz[col] = colValid ? cy * cz : 0;
+        }
+        const int s9 = e / 3, j = e % 3, dy = s9 / 3 - 1, dz = s9 % 3 - 1;
+        const bool ok = colValid && e < 27 && iy + dy >= 0 && iy + dy < NY && iz + dz >= 0 && iz + dz < NZ;
+        laneOff[t] = ok ? 3 * ((dy + (iy > 0 ? 1 : 0)) * cz + dz + (iz > 0 ? 1 : 0)) + j : -1;
+    }
+    __syncthreads();  // the only CTA-wide barrier: from here on the warps are ordered by dataflow flags
+
+    double* lo0 = seg0a;
+    double* hi0 = seg0b;
+    double* pfLo = pfA;
+    double* pfHi = pfB;
+    const int64_t cstride = (int64_t)A.nX * A.nY * A.nZ * 8;
+    const double* __restrict__ uSrc = TL ? A.U : A.dU;
+    const int64_t totYZ = (int64_t)totY * totZ;
+
+    if (warp >= NW) {
+        // ===================== producer warps: phase A, one plane step ahead =====================
+        const int j = warp - NW;
+        double* stageBuf = stageAll + j * 216;  // two staging buffers: the next task's nodal data travels during the current one
+        const unsigned stageAddr0 = (unsigned)__cvta_generic_to_shared(stageBuf);
+        const int planeStride3 = 3 * NY * NZ;
+        const int ak = lane >> 3, agp = lane & 7;
+        constexpr int TPS = (NW + NWP - 1) / NWP;  // tasks (patches) per plane step of one producer
+        const int nSteps = exEnd - exBegin + 1;
+        const int nTasks = nSteps * TPS;
+        // issue the asynchronous copies (nodal x,u) and the L2 prefetch (Gauss-point state) of task t
+        auto issue = [&](int t) {
+            const int st = t / TPS, p = j + (t % TPS) * NWP;
+            if (t < nTasks && p < NW) {
+                const int exs = exBegin + st;
+                const int pyq = p / NPZ, pzq = p % NPZ;
+                if (lane < 18) {
+                    const int X = lane / 9, Y = (lane / 3) % 3, Z = lane % 3;
+                    const int iy = y0 - 1 + 2 * pyq + Y, iz = z0 - 1 + 2 * pzq + Z;
+                    if (iy >= 0 && iy < NY && iz >= 0 && iz < NZ) {
+                        const int64_t o = (int64_t)exs * planeStride3 + 3 * ((X * NY + iy) * NZ + iz);
+                        const unsigned dst = stageAddr0 + (unsigned)(t & 1) * 864u + 48u * lane;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * c), "l"(A.coords + o + c) : "memory");
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 24u + 8u * c), "l"(uSrc + o + c) : "memory");
+                        }
+                    }
+                }
+                const int apy = 2 * pyq + (ak >> 1), apz = 2 * pzq + (ak & 1);
+                const int aey = y0 - 1 + apy, aez = z0 - 1 + apz;
+                if (aey >= 0 && aey < A.nY && aez >= 0 && aez < A.nZ && apy <= ny && apz <= nz) {
+                    const double* sp = A.stateRef + (((int64_t)exs * A.nY + aey) * A.nZ + aez) * 8 + agp;
+#pragma unroll
+                    for (int c = 0; c < 12 + (MC != MC_LE ? 1 : 0); ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + c * cstride));
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        issue(0);
+#pragma unroll 1
+        for (int t = 0; t < nTasks; ++t) {
+            issue(t + 1);
+            const int step = t / TPS, p = j + (t % TPS) * NWP;
+            if (p >= NW) {
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                continue;
+            }
+            const int ex = exBegin + step;
+            const int pyq = p / NPZ, pzq = p % NPZ;
+            // the record buffer (step & 1) of this patch must have been consumed (it last held plane step - 2)
+            waitFlags(consumedCnt, p, lane == 0, step - 1, A.failFlag, A.spinNs);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
+            const double* stage = stageBuf + (t & 1) * 108;
+            const int apy = 2 * pyq + (ak >> 1), apz = 2 * pzq + (ak & 1);
+            const int aey = y0 - 1 + apy, aez = z0 - 1 + apz;
+            const bool aValid = aey >= 0 && aey < A.nY && aez >= 0 && aez < A.nZ && apy <= ny && apz <= nz;
+            if (aValid) {
+                double* rec = tables + ((size_t)((step & 1) * NW + p) * 4 + ak) * R::PER_EL + agp * R::RS;
+                const int64_t e = ((int64_t)ex * A.nY + aey) * A.nZ + aez;
+                const int64_t off = e * 8 + agp;
+                const bool writeState = ex >= xa && apy >= 1 && apz >= 1;
+                gaussPointCompact<MC, TL>(rec, stage + ((ak >> 1) * 3 + (ak & 1)) * 6, agp, A.mp, A.stateRef + off, A.stateTemp + off, cstride,
+                                          writeState, A.failFlag);
+            }
+            EWB_SMEM_FENCE();
+            __syncwarp();
+            if (lane == 0) producedCnt[p] = step + 1;
+        }
+        return;
+    }
+    // ===================== consumer warps: one per patch =====================
+    // this warp's patch and its dependencies
+    const int p = warp, pyq = p / NPZ, pzq = p % NPZ;
+    // (1) accumulation of round R waits for the 8 neighbouring patches to have finished round R-1
+    int depN = 0; bool hasN = false;
+    if (lane < 9) {
+        const int qy = pyq + lane / 3 - 1, qz = pzq + lane % 3 - 1;
+        hasN = lane != 4 && qy >= 0 && qy < NPY && qz >= 0 && qz < NPZ;
+        depN = hasN ? qy * NPZ + qz : 0;
+    }
+    // (2) the first accumulation of a plane step waits for the owners of the columns it touches to have flushed the previous step
+    int depF = 0; bool hasF = false;
+    if (lane < 4) {
+        const int qy = pyq - (lane >> 1), qz = pzq - (lane & 1);
+        hasF = qy >= 0 && qz >= 0;
+        depF = hasF ? qy * NPZ + qz : 0;
+    }
+    // (3) the flush of this warp's columns (2pyq+{0,1}, 2pzq+{0,1}) waits for the patches that touch them
+    int depD = 0; bool hasD = false;
+    if (lane < 4) {
+        const int qy = pyq + (lane >> 1), qz = pzq + (lane & 1);
+        hasD = qy < NPY && qz < NPZ;
+        depD = hasD ? qy * NPZ + qz : 0;
+    }
+
+    // ---- lane constants of phase B ----
+    const int bRow = lane >> 2, bq = lane & 3;
+    const int na = rowNode(bRow);  // node of this lane's mma row
+    double dNl[2][3];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        double xi, eta, zeta, w;
+        Gauss<8>::get(4 * ks + bq, xi, eta, zeta, w);
+        const double sa = NodeLC<8>::xi(na), sb = NodeLC<8>::eta(na), sc = NodeLC<8>::zeta(na);
+        const double fx = 1.0 + sa * xi, fe = 1.0 + sb * eta, fz = 1.0 + sc * zeta;
+        dNl[ks][0] = 0.125 * sb * fx * fz;
+        dNl[ks][1] = 0.125 * sa * fe * fz;
+        dNl[ks][2] = 0.125 * sc * fx * fe;
+    }
+    // accumulation targets of the two blocks of this lane: segment selector and offset inside the tile image
+    int accOff[2];
+    bool accSame[2];  // block stays in the node plane of a (dx = 0 segment) or crosses to the other plane
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int nb = rowNode(2 * bq + t);
+        const int ry = ndy(nb) - ndy(na), rz = ndz(nb) - ndz(na);
+        accSame[t] = ndx(nb) == ndx(na);
+        accOff[t] = (ndy(na) * TZ + ndz(na)) * CS + ((ry + 1) * 3 + rz + 1) * 3;
+    }
+    const bool aHi = ndx(na) != 0;
+
+    // flush the finished segments (nullptr = not finished) of this warp's owned nodes of plane ix, clear them
+    auto flushPlane = [&](int ix, double* sM, double* s0, double* sP, double* pf) {
+        const int cx = (ix > 0) + 1 + (ix < NX - 1);
+        double* xbase = A.data + 9 * (int64_t)pre(ix) * totYZ;
+        const int rx0 = ix > 0 ? 1 : 0;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int ly_ = 2 * pyq + (cc >> 1), lz_ = 2 * pzq + (cc & 1);
+            if (ly_ >= TY || lz_ >= TZ) continue;
+            const int col = ly_ * TZ + lz_;
+            const int cycz = colCycz[col];
+            if (cycz == 0) continue;
+            const int lo = laneOff[col * 32 + lane];
+            double* rowBase = xbase + ((int64_t)(9 * cx) * colPart[col] + lo);
+            const int rowStride = 3 * cx * cycz;
+            if (A.wantK && lane < 27) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    double* seg = d == 0 ? sM : (d == 1 ? s0 : sP);
+                    if (seg == nullptr) continue;
+                    const int dx = d - 1;
+                    const bool ok = ix + dx >= 0 && ix + dx < NX && lo >= 0;
+                    double* src = seg + col * CS + lane;
+                    double* dst = rowBase + 3 * ((dx + rx0) * cycz);
+                    const double v0 = src[0], v1 = src[27], v2 = src[54];
+                    src[0] = 0.0;
+                    src[27] = 0.0;
+                    src[54] = 0.0;
+                    if (ok) {
+                        dst[0] = v0;
+                        dst[rowStride] = v1;
+                        dst[2 * rowStride] = v2;
+                    }
+                }
+            }
+            if (pf != nullptr && lane < 3) {
+                const double pv = pf[col * 6 + lane], fv = pf[col * 6 + 3 + lane];
+                pf[col * 6 + lane] = 0.0;
+                pf[col * 6 + 3 + lane] = 0.0;
+                const int ly = 2 * pyq + (cc >> 1), lz = 2 * pzq + (cc & 1);
+                const int64_t dof = 3 * ((((int64_t)ix * NY + (y0 + ly)) * NZ) + (z0 + lz)) + lane;
+                if (A.accumulatePF) {
+                    A.P[dof] += pv;
+                    A.F[dof] += fv;
+                } else {
+                    A.P[dof] = pv;
+                    A.F[dof] = fv;
+                }
+            }
+        }
+    };
+
+#ifdef EWB_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tsubA[4] = {0, 0, 0, 0};
+    const long long tstart = clock64();
+#endif
+    // per-round loop invariants: element validity (warp uniform), ownership of this lane's row node, tile-image offset
+    unsigned validMask = 0, ownMask = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int py = 2 * pyq + (k >> 1), pz = 2 * pzq + (k & 1);
+        const int ey = y0 - 1 + py, ez = z0 - 1 + pz;
+        if (ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && py <= ny && pz <= nz) validMask |= 1u << k;
+        const int ly = py - 1 + ndy(na), lz = pz - 1 + ndz(na);
+        if (ly >= 0 && ly < ny && lz >= 0 && lz < nz) ownMask |= 1u << k;
+    }
+    const int eOff0 = (2 * pyq - 1) * TZ + (2 * pzq - 1);
+
+    int step = 0;
+    for (int ex = exBegin; ex <= exEnd; ++ex, ++step) {
+        const bool loOwned = ex >= xa, hiOwned = (ex + 1) < xb;
+        // the producers publish this plane step's Gauss-point records
+        EWB_TIC(tWP);
+        waitFlags(producedCnt, p, lane == 0, step + 1, A.failFlag, A.spinNs);
+        EWB_ACC(0, tWP);
+        const double* wt = tables + (size_t)((step & 1) * NW + p) * 4 * R::PER_EL;
+        // per-step accumulation bases of this lane (segments rotate every plane)
+        double* accBase[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) accBase[t] = (aHi ? (accSame[t] ? hi0 : segM) : (accSame[t] ? lo0 : segP)) + accOff[t];
+        double* pfBase = (aHi ? pfHi : pfLo) + (ndy(na) * TZ + ndz(na)) * 6;
+        const bool planeOwned = aHi ? hiOwned : loOwned;
+        // ------------- phase B: 4 colour rounds, one element per round -------------
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const int Rnd = 4 * step + k;
+            const bool valid = (validMask >> k) & 1;
+            double K0[9], K1[9], Pr[3];
+            // ---- ordering: same-colour elements of different patches never share a node.  With registers to spare the
+            // blocks are computed BEFORE the wait, so a fast warp's tensor work overlaps its neighbours' accumulation. ----
+            EWB_TIC(tB);
+            if (COMPUTE_FIRST && valid) elementBlocks<MC>(wt + k * R::PER_EL, lane, dNl, A.mp, A.wantK != 0, K0, K1, Pr);
+            if (COMPUTE_FIRST && k == 3) {  // all four elements' records are consumed: the producers may refill this buffer
+                __syncwarp();
+                if (lane == 0) consumedCnt[p] = step + 1;
+            }
+            EWB_ACC(2, tB);
+            EWB_TIC(tW);
+            if (k == 0) waitFlags(flushedCnt, depF, hasF, step, A.failFlag, A.spinNs);
+            waitFlags(doneCnt, depN, hasN, Rnd, A.failFlag, A.spinNs);
+            EWB_ACC(1, tW);
+            if (!COMPUTE_FIRST && valid) elementBlocks<MC>(wt + k * R::PER_EL, lane, dNl, A.mp, A.wantK != 0, K0, K1, Pr);
+            if (!COMPUTE_FIRST && k == 3) {  // all four elements' records are consumed: the producers may refill this buffer
+                __syncwarp();
+                if (lane == 0) consumedCnt[p] = step + 1;
+            }
+            EWB_TIC(tE);
+            if (valid) {
+                if (planeOwned && ((ownMask >> k) & 1)) {
+                    const int eOff = eOff0 + (k >> 1) * TZ + (k & 1);
+                    if (bq == 0) {
+                        double* pf = pfBase + eOff * 6;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            pf[i] += Pr[i];
+                            pf[3 + i] += fabs(Pr[i]);
+                        }
+                    }
+                    if (A.wantK) {
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            double* dst = accBase[t] + eOff * CS;
+                            const double* Kt = t ? K1 : K0;
+#pragma unroll
+                            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                                for (int j = 0; j < 3; ++j) dst[i * 27 + j] += Kt[i * 3 + j];
+                        }
+                    }
+                }
+            }
+            EWB_SMEM_FENCE();
+            __syncwarp();
+            if (lane == 0) doneCnt[p] = Rnd + 1;
+            EWB_ACC(3, tE);
+        }
+        // ---------------- flush this warp's finished columns, rotate ----------------
+        EWB_TIC(tWF);
+        waitFlags(doneCnt, depD, hasD, 4 * (step + 1), A.failFlag, A.spinNs);
+        EWB_ACC(4, tWF);
+        EWB_TIC(tF);
+        if (loOwned) flushPlane(ex, nullptr, lo0, segP, pfLo);
+        if (hiOwned) flushPlane(ex + 1, segM, nullptr, nullptr, nullptr);
+        if (ex == exEnd && xb == NX) flushPlane(NX - 1, nullptr, hi0, nullptr, pfHi);  // last node plane: nothing above it
+        EWB_SMEM_FENCE();
+        __syncwarp();
+        if (lane == 0) flushedCnt[p] = step + 1;
+        EWB_ACC(5, tF);
+        {
+            double* t0 = lo0; lo0 = hi0; hi0 = t0;
+            double* t1 = pfLo; pfLo = pfHi; pfHi = t1;
+        }
+    }
+#ifdef EWB_TIMING
+    if (A.timing != nullptr && lane == 0) {
+        tacc[6] = clock64() - tstart;
+        tacc[7] = step;
+        for (int i = 0; i < 8; ++i) A.timing[((size_t)blockIdx.x * NW + warp) * 12 + i] = tacc[i];
+        for (int i = 0; i < 4; ++i) A.timing[((size_t)blockIdx.x * NW + warp) * 12 + 8 + i] = tsubA[i];
+    }
+#endif
+}
+
 struct SweepPlan {
     int64_t nX = 0, nY = 0, nZ = 0;
     const int64_t* adjPtr = nullptr;  // unused by the kernel (closed-form row bases); kept for debugging
@@ -785,18 +1150,14 @@ struct SweepPlan {
     }
     void release() {}
 
-    template <int MC, bool TL, int TY, int TZ>
-    int launchT(const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st) {
-        using Rec = RecLayout<MC>;
-        constexpr int NW_ = ((TY + 1) / 2) * ((TZ + 1) / 2);
-        (void)NW_;
-        if ((nX + 1) * (nY + 1) * (nZ + 1) >= ((int64_t)1 << 31) / 3) return EWB_ERR_UNSUPPORTED;  // int32 node indexing inside the kernel
-        SweepArgs a;
+    template <int TY, int TZ>
+    int fillArgs(SweepArgs& a, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st, int NW_) {
+        (void)st; (void)NW_;
+        const int64_t tiles = (int64_t)((nY + 1 + TY - 1) / TY) * ((nZ + 1 + TZ - 1) / TZ);
         a.nX = (int)nX; a.nY = (int)nY; a.nZ = (int)nZ;
         a.tilesY = (int)((nY + 1 + TY - 1) / TY);
         a.tilesZ = (int)((nZ + 1 + TZ - 1) / TZ);
         // chunks along x: minimise (number of CTA rounds on nSM SMs) x (planes per chunk incl. the halo plane)
-        const int64_t tiles = (int64_t)a.tilesY * a.tilesZ;
         int best = 1;
         double bestCost = 1e300;
         for (int c = 1; c <= 64 && (nX + 1) / c >= 6; ++c) {
@@ -825,12 +1186,38 @@ struct SweepPlan {
         a.data = b->csr_data; a.P = b->P; a.F = b->F; a.mp = mp; a.failFlag = failFlag;
         a.wantK = (flags & EWB_FLAG_NO_STIFFNESS) ? 0 : 1;
         a.accumulatePF = (flags & EWB_FLAG_ACCUMULATE_PF) ? 1 : 0;
+        return EWB_OK;
+    }
+
+    template <int MC, bool TL, int TY, int TZ>
+    int launchT(const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st) {
+        using Rec = RecLayout<MC>;
+        constexpr int NW_ = ((TY + 1) / 2) * ((TZ + 1) / 2);
+        (void)NW_;
+        if ((nX + 1) * (nY + 1) * (nZ + 1) >= ((int64_t)1 << 31) / 3) return EWB_ERR_UNSUPPORTED;  // int32 node indexing inside the kernel
+        SweepArgs a;
+        if (int rc = fillArgs<TY, TZ>(a, mp, b, failFlag, flags, st, NW_)) return rc;
         constexpr int NW = ((TY + 1) / 2) * ((TZ + 1) / 2);
         auto kern = sweepKernel<MC, TL, TY, TZ>;
         const size_t smem = ((size_t)AccLayout<TY, TZ>::TABLES + (size_t)NW * 4 * Rec::PER_EL + (size_t)NW * 108) * sizeof(double);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EWB_ERR_CUDA;
-        const int64_t grid = tiles * a.nChunks;
+        const int64_t grid = (int64_t)a.tilesY * a.tilesZ * a.nChunks;
         kern<<<(unsigned)grid, NW * 32, smem, st>>>(a);
+        return cudaGetLastError() == cudaSuccess ? EWB_OK : EWB_ERR_CUDA;
+    }
+
+    template <int MC, bool TL, int TY, int TZ, int NWP>
+    int launchPC(const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st) {
+        using Rec = RecLayout<MC>;
+        constexpr int NW_ = ((TY + 1) / 2) * ((TZ + 1) / 2);
+        if ((nX + 1) * (nY + 1) * (nZ + 1) >= ((int64_t)1 << 31) / 3) return EWB_ERR_UNSUPPORTED;
+        SweepArgs a;
+        if (int rc = fillArgs<TY, TZ>(a, mp, b, failFlag, flags, st, NW_)) return rc;
+        auto kern = sweepKernelPC<MC, TL, TY, TZ, NWP>;
+        const size_t smem = ((size_t)AccLayout<TY, TZ>::TABLES + (size_t)2 * NW_ * 4 * Rec::PER_EL + (size_t)NWP * 216 + 32) * sizeof(double);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EWB_ERR_CUDA;
+        const int64_t grid = (int64_t)a.tilesY * a.tilesZ * a.nChunks;
+        kern<<<(unsigned)grid, (NW_ + NWP) * 32, smem, st>>>(a);
         return cudaGetLastError() == cudaSuccess ? EWB_OK : EWB_ERR_CUDA;
     }
 
@@ -843,7 +1230,11 @@ struct SweepPlan {
             else if (tile == 55) rc = launchT<MC_LE, false, 5, 5>(mp, b, failFlag, flags, st);
             else if (tile == 95) rc = launchT<MC_LE, false, 9, 5>(mp, b, failFlag, flags, st);
             else if (tile == 57) rc = launchT<MC_LE, false, 5, 7>(mp, b, failFlag, flags, st);
-            else rc = launchT<MC_LE, false, 7, 5>(mp, b, failFlag, flags, st);
+            else if (tile == 754) rc = launchPC<MC_LE, false, 7, 5, 4>(mp, b, failFlag, flags, st);
+            else if (tile == 753) rc = launchPC<MC_LE, false, 7, 5, 3>(mp, b, failFlag, flags, st);
+            else if (tile == 752) rc = launchPC<MC_LE, false, 7, 5, 2>(mp, b, failFlag, flags, st);
+            else if (tile == 75) rc = launchT<MC_LE, false, 7, 5>(mp, b, failFlag, flags, st);
+            else rc = launchPC<MC_LE, false, 7, 5, 4>(mp, b, failFlag, flags, st);
         }
         else if (elType == EWB_C3D8 && mc == MC_VM) rc = launchT<MC_VM, false, 7, 5>(mp, b, failFlag, flags, st);
         else if (elType == EWB_C3D8TL && mc == MC_NH) rc = launchT<MC_NH, true, 7, 5>(mp, b, failFlag, flags, st);
