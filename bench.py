@@ -75,26 +75,54 @@ def make_inputs(kind, coords, n, l, seed=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML
+    (nvidia_ml_py) every 5 ms, falling back to polling `nvidia-smi` when NVML is unavailable."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.samples = []  # (sm_mhz, power_w, reasons set)
+        self.sm_max = None
         self.stop = False
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
         self.t = threading.Thread(target=self.run, daemon=True)
+
+    def _nvml_sample(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(self.h))
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        return sm, pw, {k for k, bit in names.items() if mask & bit}
 
     def run(self):
         while not self.stop:
             try:
+                if self.nvml is not None:
+                    self.samples.append(self._nvml_sample())
+                    time.sleep(0.005)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                    f = [x.strip() for x in out.split(",")]
+                    self.sm_max = float(f[1])
+                    reasons = {nme for nme, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]) if v.lower().startswith("active")}
+                    self.samples.append((float(f[0]), float(f[2]), reasons))
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def __enter__(self):
         self.t.start()
@@ -106,15 +134,13 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"]}
+        sm = sorted(s[0] for s in self.samples)
         reasons = set()
         for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "power_w_max": max(float(s[2]) for s in self.samples),
-                "samples": len(sm), "reasons": sorted(reasons)}
+            reasons |= s[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max, "power_w_max": max(s[1] for s in self.samples),
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi", "reasons": sorted(reasons)}
 
 
 def cpu_reference_leg(wl, sample_n, steps, warmup):
