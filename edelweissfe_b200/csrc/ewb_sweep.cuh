@@ -1224,7 +1224,7 @@ struct SweepPlan {
     int launch(int elType, int mc, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st, int* launches) {
         int rc = EWB_ERR_UNSUPPORTED;
         const char* tileEnv = getenv("EWB_TILE");
-        const int tile = tileEnv ? atoi(tileEnv) : 75;
+        const int tile = tileEnv ? atoi(tileEnv) : 754;  // default: producer/consumer kernel, 7x5 tile, 4 producer warps
         if (elType == EWB_C3D8 && mc == MC_LE) {
             if (tile == 77) rc = launchT<MC_LE, false, 7, 7>(mp, b, failFlag, flags, st);
             else if (tile == 55) rc = launchT<MC_LE, false, 5, 5>(mp, b, failFlag, flags, st);
