@@ -242,3 +242,36 @@ def test_full_size_properties(workload):
         kappa = S1[12]
         frac = float((kappa > 0).double().mean())
         assert 0.3 < frac < 0.7  # the recipe yields roughly half of the Gauss points
+
+
+@pytest.mark.parametrize("n", [(1, 1, 1), (1, 1, 6), (2, 1, 1), (1, 7, 1), (6, 2, 13), (13, 6, 2), (35, 3, 3), (8, 15, 11)])
+@pytest.mark.parametrize("material", ["linearelastic", "vonmises"])
+def test_sweep_edge_shapes(n, material):
+    """Degenerate and ragged boxes: tiles larger than the mesh, single element planes, several x-chunks,
+    tile edges that coincide with the mesh boundary (producer/consumer and single-role kernels)."""
+    import torch
+
+    from edelweissfe_b200 import ElementAssembly, box_mesh
+    from oracle import port
+
+    props = [2.1e4, 0.22] if material == "linearelastic" else [2.1e4, 0.22, 355, 1000, 200, 1400]
+    coords, conn = box_mesh(*n, lX=1.0 * n[0], lY=1.2 * n[1], lZ=0.8 * n[2])
+    rng = np.random.default_rng(7)
+    coords = coords + 0.1 * rng.uniform(-1, 1, coords.shape)
+    dU = 6e-3 * rng.standard_normal(3 * coords.shape[0])
+    asm = ElementAssembly("C3D8", conn, coords, material, props, box=n)
+    asm.U.copy_(torch.as_tensor(dU))
+    asm.dU.copy_(torch.as_tensor(dU))
+    # poison the outputs: every value must be overwritten exactly once
+    asm.csr_data.fill_(float("nan"))
+    asm.P.fill_(float("nan"))
+    asm.F.fill_(float("nan"))
+    asm.state_temp.fill_(float("nan"))
+    asm.assemble()
+    asm.poll()
+    state = np.zeros((conn.shape[0], 8, 12 + port.MATERIAL_NSTATE[material]))
+    o = port.assemble("C3D8", material, props, coords, conn, dU, dU, state, want_vij=False)
+    assert relerr(asm.csr_data.cpu().numpy(), o["data"]) < TOL
+    assert relerr(asm.P.cpu().numpy(), o["P"]) < TOL
+    assert relerr(asm.F.cpu().numpy(), o["F"]) < TOL
+    assert relerr(asm.state_aos("temp").cpu().numpy(), o["stateTemp"]) < TOL
