@@ -12,6 +12,7 @@
 #include "../../include/edelweiss_b200.h"
 #include "ewb_generic.cuh"
 #include "ewb_sweep.cuh"
+#include "ewb_staged.cuh"
 
 namespace {
 
@@ -65,6 +66,7 @@ struct ewb_plan {
     int64_t nX = 0, nY = 0, nZ = 0;
     std::vector<int32_t> connHost;
     ewb::SweepPlan sweep;
+    ewb::StagedPlan staged;
 };
 
 namespace {
@@ -212,6 +214,7 @@ void ewb_plan_destroy(ewb_plan* p) {
     cudaFree(p->failFlag); cudaFree(p->peScratch); cudaFree(p->vijScratch);
     if (p->failHost) cudaFreeHost(p->failHost);
     p->sweep.release();
+    p->staged.release();
     delete p;
 }
 
@@ -387,6 +390,14 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
 
     if (p->isBox && !(flags & EWB_FLAG_FORCE_GENERIC) && b->vij == nullptr) {
         int launches = 0;
+        const char* pathEnv = getenv("EWB_PATH");  // "sweep" (fused) or "staged" (two streaming kernels)
+        const bool useStaged = (flags & EWB_FLAG_STAGED) || (pathEnv && std::string(pathEnv) == "staged");
+        if (useStaged) {
+            int rcS = p->staged.launch(p->elType, mc, p->nEl, p->nX, p->nY, p->nZ, p->conn, mp, b, p->failFlag, flags, st, &launches);
+            g_launches += launches;
+            if (rcS == EWB_OK) return EWB_OK;
+            if (rcS != EWB_ERR_UNSUPPORTED) return fail(rcS, std::string("staged launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        }
         int rc = p->sweep.launch(p->elType, mc, mp, b, p->failFlag, flags, st, &launches);
         g_launches += launches;
         if (rc == EWB_OK) return EWB_OK;

@@ -84,7 +84,8 @@ __device__ __forceinline__ int rowNode(int r) { return (0x67542310u >> (4 * r)) 
 // ---------------------------------------------------------------------------------------------
 // stg: the warp's staged nodal data [18 patch nodes][x,y,z,u0,u1,u2], already offset to this lane's element
 // (patch node of local node a = stg + (9 dx + 3 dy + dz) * 6).
-template <int MC, bool TL>
+// LINEAR: stg holds the element's own 8 nodes [a][x,y,z,u0,u1,u2] instead of the 3x3x2 patch image.
+template <int MC, bool TL, bool LINEAR = false>
 __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg, int gp, const MatParams& mp,
                                                   const double* __restrict__ state_ref, double* __restrict__ state_temp, int64_t cstride,
                                                   bool writeState, int* failFlag, long long* tsub = nullptr) {
@@ -114,7 +115,7 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
         constexpr int a = decltype(ic)::value;
         double d[3];
         shapeDeriv<8, a>(xi, eta, zeta, d);
-        constexpr int so = (((a >> 1) & 1) * 9 + ((a >> 2) & 1) * 3 + ((a ^ (a >> 1)) & 1)) * 6;
+        constexpr int so = LINEAR ? a * 6 : (((a >> 1) & 1) * 9 + ((a >> 2) & 1) * 3 + ((a ^ (a >> 1)) & 1)) * 6;
         const double x0 = stg[so], x1 = stg[so + 1], x2 = stg[so + 2];
         const double u0 = stg[so + 3], u1 = stg[so + 4], u2 = stg[so + 5];
 #pragma unroll

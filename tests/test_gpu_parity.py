@@ -71,7 +71,7 @@ def test_golden(name, path):
         ("C3D20", "vonmises", [2.1e4, 0.22, 355, 1000, 200, 1400], (3, 3, 4), 5e-3),
     ],
 )
-@pytest.mark.parametrize("path", ["generic", "auto"])
+@pytest.mark.parametrize("path", ["generic", "auto", "staged"])
 def test_against_oracle_seeded(elType, material, props, n, scale, path):
     import torch
 
@@ -79,16 +79,16 @@ def test_against_oracle_seeded(elType, material, props, n, scale, path):
     from oracle import port
 
     nn = 20 if "20" in elType else 8
-    if path == "auto" and nn != 8:
-        pytest.skip("structured sweep is Hexa8 only")
+    if path != "generic" and nn != 8:
+        pytest.skip("structured paths are Hexa8 only")
     coords, conn = box_mesh(*n, lX=float(n[0]), lY=1.1 * n[1], lZ=0.9 * n[2], elType=elType)
     c2, conn2 = port.boxgen(*n, float(n[0]), 1.1 * n[1], 0.9 * n[2], nnodes=nn)
     assert np.array_equal(conn, conn2) and np.array_equal(coords, c2)
     rng = np.random.default_rng(1)
     if nn == 8:
         coords = coords + 0.15 * rng.uniform(-1, 1, coords.shape)
-    asm = ElementAssembly(elType, conn, coords, material, props, box=n if path == "auto" else None)
-    flags = _lib.EWB_FLAG_FORCE_GENERIC if path == "generic" else 0
+    asm = ElementAssembly(elType, conn, coords, material, props, box=n if path != "generic" else None)
+    flags = {"generic": _lib.EWB_FLAG_FORCE_GENERIC, "auto": 0, "staged": _lib.EWB_FLAG_STAGED}[path]
     nGp = 27 if nn == 20 else 8
     state = np.zeros((conn.shape[0], nGp, 12 + port.MATERIAL_NSTATE[material]))
     U = np.zeros(3 * coords.shape[0])
@@ -246,7 +246,8 @@ def test_full_size_properties(workload):
 
 @pytest.mark.parametrize("n", [(1, 1, 1), (1, 1, 6), (2, 1, 1), (1, 7, 1), (6, 2, 13), (13, 6, 2), (35, 3, 3), (8, 15, 11)])
 @pytest.mark.parametrize("material", ["linearelastic", "vonmises"])
-def test_sweep_edge_shapes(n, material):
+@pytest.mark.parametrize("path", ["sweep", "staged"])
+def test_sweep_edge_shapes(n, material, path):
     """Degenerate and ragged boxes: tiles larger than the mesh, single element planes, several x-chunks,
     tile edges that coincide with the mesh boundary (producer/consumer and single-role kernels)."""
     import torch
@@ -267,7 +268,9 @@ def test_sweep_edge_shapes(n, material):
     asm.P.fill_(float("nan"))
     asm.F.fill_(float("nan"))
     asm.state_temp.fill_(float("nan"))
-    asm.assemble()
+    from edelweissfe_b200 import _lib
+
+    asm.assemble(_lib.EWB_FLAG_STAGED if path == "staged" else 0)
     asm.poll()
     state = np.zeros((conn.shape[0], 8, 12 + port.MATERIAL_NSTATE[material]))
     o = port.assemble("C3D8", material, props, coords, conn, dU, dU, state, want_vij=False)
