@@ -223,9 +223,15 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
 // rowNode(2q+t): returns K0 = K[a][b_0], K1 = K[a][b_1] and (in all 4 lanes of the row) the residual
 // row Pr of node a.  dNl[ks][r]: lane-constant dN_a/d(eta,xi,zeta) at Gauss point 4ks+q.
 // ---------------------------------------------------------------------------------------------
+// raw tensor-pipe accumulators of one element in one lane (two node blocks: t = 0, 1)
+template <int MC> struct TileAcc;
+template <> struct TileAcc<MC_LE> { double c[3][3][2]; };
+template <> struct TileAcc<MC_VM> { double c1[3][3][2], c2[3][3][2]; };
+template <> struct TileAcc<MC_NH> { double c1[3][3][2], c2[3][3][2], d0[3][2]; };
+
 template <int MC>
-__device__ __forceinline__ void elementBlocks(const double* T, int lane, const double (&dNl)[2][3], const MatParams& mp, bool wantK,
-                                              double (&K0)[9], double (&K1)[9], double (&Pr)[3]) {
+__device__ __forceinline__ void elementTiles(const double* T, int lane, const double (&dNl)[2][3], const MatParams& mp, bool wantK,
+                                             TileAcc<MC>& acc, double (&Pr)[3]) {
     using R = RecLayout<MC>;
     const int q = lane & 3;
     double g[2][3];
@@ -239,7 +245,7 @@ __device__ __forceinline__ void elementBlocks(const double* T, int lane, const d
         for (int c = 0; c < 3; ++c) g[ks][c] = rec[c * 3] * dNl[ks][0] + rec[c * 3 + 1] * dNl[ks][1] + rec[c * 3 + 2] * dNl[ks][2];
     }
     if constexpr (MC == MC_LE) {
-        double c[3][3][2];
+        auto& c = acc.c;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -261,24 +267,9 @@ __device__ __forceinline__ void elementBlocks(const double* T, int lane, const d
                 }
             }
         }
-        const double lpm = mp.lambda + mp.G;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            double* Kt = t ? K1 : K0;
-            const double tr = mp.G * (c[0][0][t] + c[1][1][t] + c[2][2][t]);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                Kt[i * 3 + i] = fma(lpm, c[i][i][t], tr);
-#pragma unroll
-                for (int j = i + 1; j < 3; ++j) {
-                    const double x = c[i][j][t], y = c[j][i][t];
-                    Kt[i * 3 + j] = fma(mp.lambda, x, mp.G * y);
-                    Kt[j * 3 + i] = fma(mp.lambda, y, mp.G * x);
-                }
-            }
-        }
     } else if constexpr (MC == MC_VM) {
-        double c1[3][3][2], c2[3][3][2];
+        auto& c1 = acc.c1;
+        auto& c2 = acc.c2;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -310,17 +301,10 @@ __device__ __forceinline__ void elementBlocks(const double* T, int lane, const d
                 }
             }
         }
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            double* Kt = t ? K1 : K0;
-            const double tr = c2[0][0][t] + c2[1][1][t] + c2[2][2][t];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = c1[i][j][t] + c2[j][i][t] + (i == j ? tr : 0.0);
-        }
     } else {
-        double c1[3][3][2], c2[3][3][2], d0[3][2];
+        auto& c1 = acc.c1;
+        auto& c2 = acc.c2;
+        auto& d0 = acc.d0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             d0[i][0] = d0[i][1] = 0.0;
@@ -366,15 +350,6 @@ __device__ __forceinline__ void elementBlocks(const double* T, int lane, const d
                 }
             }
         }
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            double* Kt = t ? K1 : K0;
-            const double tr = d0[0][t] + d0[1][t] + d0[2][t];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = c1[i][j][t] + c2[j][i][t] + (i == j ? tr : 0.0);
-        }
     }
     // reduce the residual row over the 4 lanes (Gauss-point pairs) of the row
 #pragma unroll
@@ -382,6 +357,47 @@ __device__ __forceinline__ void elementBlocks(const double* T, int lane, const d
         Pr[i] += __shfl_xor_sync(0xffffffffu, Pr[i], 1);
         Pr[i] += __shfl_xor_sync(0xffffffffu, Pr[i], 2);
     }
+}
+
+// tangent assembly of node block t (0/1) of the lane from the raw accumulators: Kt[i*3+j] = Ke[3a+i][3b_t+j]
+template <int MC>
+__device__ __forceinline__ void finishBlock(const TileAcc<MC>& acc, int t, const MatParams& mp, double (&Kt)[9]) {
+    if constexpr (MC == MC_LE) {
+        const auto& c = acc.c;
+        const double lpm = mp.lambda + mp.G;
+        const double tr = mp.G * (c[0][0][t] + c[1][1][t] + c[2][2][t]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            Kt[i * 3 + i] = fma(lpm, c[i][i][t], tr);
+#pragma unroll
+            for (int j = i + 1; j < 3; ++j) {
+                const double x = c[i][j][t], y = c[j][i][t];
+                Kt[i * 3 + j] = fma(mp.lambda, x, mp.G * y);
+                Kt[j * 3 + i] = fma(mp.lambda, y, mp.G * x);
+            }
+        }
+    } else if constexpr (MC == MC_VM) {
+        const double tr = acc.c2[0][0][t] + acc.c2[1][1][t] + acc.c2[2][2][t];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = acc.c1[i][j][t] + acc.c2[j][i][t] + (i == j ? tr : 0.0);
+    } else {
+        const double tr = acc.d0[0][t] + acc.d0[1][t] + acc.d0[2][t];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = acc.c1[i][j][t] + acc.c2[j][i][t] + (i == j ? tr : 0.0);
+    }
+}
+
+template <int MC>
+__device__ __forceinline__ void elementBlocks(const double* T, int lane, const double (&dNl)[2][3], const MatParams& mp, bool wantK,
+                                              double (&K0)[9], double (&K1)[9], double (&Pr)[3]) {
+    TileAcc<MC> acc;
+    elementTiles<MC>(T, lane, dNl, mp, wantK, acc, Pr);
+    finishBlock<MC>(acc, 0, mp, K0);
+    finishBlock<MC>(acc, 1, mp, K1);
 }
 
 // Accumulator geometry (doubles).  Per node column 81 doubles per segment, laid out [i][s9][j] so that a
@@ -1072,7 +1088,8 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
             if (k == 0) waitFlags(flushedCnt, depF, hasF, step, A.failFlag, A.spinNs);
             waitFlags(doneCnt, depN, hasN, Rnd, A.failFlag, A.spinNs);
             EWB_ACC(1, tW);
-            if (!COMPUTE_FIRST && valid) elementBlocks<MC>(wt + k * R::PER_EL, lane, dNl, A.mp, A.wantK != 0, K0, K1, Pr);
+            TileAcc<MC> tacc_;
+            if (!COMPUTE_FIRST && valid) elementTiles<MC>(wt + k * R::PER_EL, lane, dNl, A.mp, A.wantK != 0, tacc_, Pr);
             if (!COMPUTE_FIRST && k == 3) {  // all four elements' records are consumed: the producers may refill this buffer
                 __syncwarp();
                 if (lane == 0) consumedCnt[p] = step + 1;
@@ -1093,7 +1110,9 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
 #pragma unroll
                         for (int t = 0; t < 2; ++t) {
                             double* dst = accBase[t] + eOff * CS;
-                            const double* Kt = t ? K1 : K0;
+                            double Kf[9];
+                            if (!COMPUTE_FIRST) finishBlock<MC>(tacc_, t, A.mp, Kf);
+                            const double* Kt = COMPUTE_FIRST ? (t ? K1 : K0) : Kf;
 #pragma unroll
                             for (int i = 0; i < 3; ++i)
 #pragma unroll
