@@ -1088,12 +1088,14 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
             if (k == 0) waitFlags(flushedCnt, depF, hasF, step, A.failFlag, A.spinNs);
             waitFlags(doneCnt, depN, hasN, Rnd, A.failFlag, A.spinNs);
             EWB_ACC(1, tW);
+            EWB_TIC(tB2);
             TileAcc<MC> tacc_;
             if (!COMPUTE_FIRST && valid) elementTiles<MC>(wt + k * R::PER_EL, lane, dNl, A.mp, A.wantK != 0, tacc_, Pr);
             if (!COMPUTE_FIRST && k == 3) {  // all four elements' records are consumed: the producers may refill this buffer
                 __syncwarp();
                 if (lane == 0) consumedCnt[p] = step + 1;
             }
+            EWB_ACC(2, tB2);
             EWB_TIC(tE);
             if (valid) {
                 if (planeOwned && ((ownMask >> k) & 1)) {

@@ -26,12 +26,12 @@ asm.poll()
 lib = asm.lib
 lib.ewb_debug_timing.restype = C.c_int64
 lib.ewb_debug_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
-NW = 16
+NW = 12
 buf = np.zeros(225 * 64 * NW * 12, dtype=np.int64)
 m = lib.ewb_debug_timing(asm.plan, buf.ctypes.data, buf.size)
 t = buf[:m].reshape(-1, NW, 12)
 t = t[t[:, 0, 7] > 0]
-names = ["phaseA", "wait_round", "elementBlocks", "emission", "wait_flush", "flush", "total", "steps", "A:loads+J,D", "A:inverse+rec", "A:material", "A:state store"]
+names = ["phaseA | wait_producer", "wait_round", "elementBlocks", "emission", "wait_flush", "flush", "total", "steps", "A:loads+J,D", "A:inverse+rec", "A:material", "A:state store"]
 print("CTAs", t.shape[0], "steps per CTA", np.unique(t[:, 0, 7]))
 full = t[t[:, :, 6].max(axis=1) > np.percentile(t[:, :, 6].max(axis=1), 50)]  # the heavier half: full tiles
 steps = full[:, :, 7].mean()
