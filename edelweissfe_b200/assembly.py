@@ -133,6 +133,18 @@ class ElementAssembly:
         check(self.lib.ewb_update_csr(self.plan, _ptr(V), _ptr(self.csr_data), self._stream()))
         return self.csr_data
 
+    def body_force(self, load, pext=None):
+        """PExt += body-force load of every element (computeBodyForces, nonlinearimplicitstatic.py:516-557).
+        pext: device tensor [nDof] (accumulated into); a zeroed one is created when omitted."""
+        if pext is None:
+            pext = torch.zeros(self.nDof, dtype=torch.float64, device=self.device)
+        ld = (C.c_double * 3)(*[float(v) for v in load])
+        check(self.lib.ewb_body_force(self.plan, _ptr(self.coords), ld, _ptr(pext), self._stream()))
+        return pext
+
+    def body_force_host(self, load):
+        return self.body_force(load).cpu().numpy()
+
     def accept_last_state(self):
         """acceptLastState for every element (element.py:373-379): stateTemp becomes stateRef."""
         self.state_ref, self.state_temp = self.state_temp, self.state_ref

@@ -428,6 +428,24 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
     return EWB_OK;
 }
 
+int ewb_body_force(ewb_plan* p, const double* coords_dev, const double load_host[3], double* pext_dev, void* stream) {
+    if (!p || !coords_dev || !load_host || !pext_dev) return fail(EWB_ERR_ARG, "ewb_body_force: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nd = 3 * p->nn;
+    if (!p->peScratch) CUDA_TRY(cudaMalloc((void**)&p->peScratch, (size_t)p->nEl * nd * sizeof(double)));
+    const int B = 128;
+    const unsigned grid = (unsigned)((p->nEl + B - 1) / B);
+    if (p->nn == 8) ewb::bodyForceKernel<8, 8><<<grid, B, 0, st>>>(p->nEl, p->conn, coords_dev, load_host[0], load_host[1], load_host[2], p->peScratch);
+    else ewb::bodyForceKernel<20, 27><<<grid, B, 0, st>>>(p->nEl, p->conn, coords_dev, load_host[0], load_host[1], load_host[2], p->peScratch);
+    LAUNCH_CHECK();
+    const unsigned g2 = (unsigned)((3 * p->nNode + 255) / 256);
+    if (p->nn == 8) ewb::gatherLoadKernel<8><<<g2, 256, 0, st>>>(p->nNode, p->incPtr, p->inc, p->peScratch, pext_dev);
+    else ewb::gatherLoadKernel<20><<<g2, 256, 0, st>>>(p->nNode, p->incPtr, p->inc, p->peScratch, pext_dev);
+    LAUNCH_CHECK();
+    return EWB_OK;
+}
+
 int ewb_poll_status(ewb_plan* p, void* stream, double* pNewDT) {
     if (!p) return fail(EWB_ERR_ARG, "null plan");
     CUDA_TRY(cudaSetDevice(p->device));

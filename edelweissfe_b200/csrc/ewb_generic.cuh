@@ -115,4 +115,77 @@ __global__ void gatherResidualKernel(int64_t nNode, const int64_t* __restrict__ 
     F[idx] = f;
 }
 
+// Shape function of node A as the reference's computeNOperator evaluates it: its node table has xi and eta
+// swapped relative to the derivative tables (displacementelement/_elementcomputationmatrices.py:164-211).
+template <int NN, int A>
+__device__ __forceinline__ double shapeFnBodyForce(double xi, double eta, double zeta) {
+    constexpr int a = NodeLC<NN>::eta(A), b = NodeLC<NN>::xi(A), c = NodeLC<NN>::zeta(A);  // swapped on purpose
+    const double fx = 1.0 + a * xi, fe = 1.0 + b * eta, fz = 1.0 + c * zeta;
+    if constexpr (NN == 8) return 0.125 * fx * fe * fz;
+    else if constexpr (a == 0) return 0.25 * (1.0 - xi * xi) * fe * fz;
+    else if constexpr (b == 0) return 0.25 * fx * (1.0 - eta * eta) * fz;
+    else if constexpr (c == 0) return 0.25 * fx * fe * (1.0 - zeta * zeta);
+    else return 0.125 * fx * fe * fz * (a * xi + b * eta + c * zeta - 2.0);
+}
+
+// computeBodyForce for every element (elements/displacementelement/element.py:348-371):
+// Pe[3a+i] = sum_gp N_a load_i detJ w.  One thread per element; Pe -> per-element slab, gathered per node afterwards.
+template <int NN, int NGP>
+__global__ void bodyForceKernel(int64_t nEl, const int32_t* __restrict__ conn, const double* __restrict__ coords, double lx, double ly, double lz,
+                                double* __restrict__ Pe) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nEl) return;
+    double X[NN * 3];
+#pragma unroll
+    for (int a = 0; a < NN; ++a) {
+        const int64_t n = conn[e * NN + a];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) X[a * 3 + c] = coords[3 * n + c];
+    }
+    double w8[NN];
+#pragma unroll
+    for (int a = 0; a < NN; ++a) w8[a] = 0.0;
+    for (int gp = 0; gp < NGP; ++gp) {
+        double xi, eta, zeta, w;
+        Gauss<NGP>::get(gp, xi, eta, zeta, w);
+        double Jm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        forNodes<NN>([&](auto ic) {
+            constexpr int a = decltype(ic)::value;
+            double d[3];
+            shapeDeriv<NN, a>(xi, eta, zeta, d);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Jm[r * 3 + c] = fma(d[r], X[a * 3 + c], Jm[r * 3 + c]);
+        });
+        const double wd = w * det3(Jm);
+        forNodes<NN>([&](auto ic) {
+            constexpr int a = decltype(ic)::value;
+            w8[a] = fma(shapeFnBodyForce<NN, a>(xi, eta, zeta), wd, w8[a]);
+        });
+    }
+#pragma unroll
+    for (int a = 0; a < NN; ++a) {
+        Pe[e * (3 * NN) + 3 * a + 0] = w8[a] * lx;
+        Pe[e * (3 * NN) + 3 * a + 1] = w8[a] * ly;
+        Pe[e * (3 * NN) + 3 * a + 2] = w8[a] * lz;
+    }
+}
+
+// PExt[el] += Pe per node in ascending element order (nonlinearimplicitstatic.py:545-553)
+template <int NN>
+__global__ void gatherLoadKernel(int64_t nNode, const int64_t* __restrict__ incPtr, const int32_t* __restrict__ inc, const double* __restrict__ Pe,
+                                 double* __restrict__ PExt) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 3 * nNode) return;
+    const int64_t A = idx / 3;
+    const int c = idx % 3;
+    double p = PExt[idx];
+    for (int64_t k = incPtr[A]; k < incPtr[A + 1]; ++k) {
+        const int32_t ea = inc[k];
+        p += Pe[(int64_t)(ea / NN) * (3 * NN) + 3 * (ea % NN) + c];
+    }
+    PExt[idx] = p;
+}
+
 }  // namespace ewb

@@ -160,6 +160,22 @@ def make_solver_class(backend_factory=default_backend):
             self.computationTimes["elements"] += _time.time() - tic
             return P, K, F
 
+        def computeBodyForces(self, bodyForces, U_np, PExt, K, timeStep):
+            """Body forces acting on ALL elements run on the device (:516-557); partial element sets stay on the host loop."""
+            tic = _time.time()
+            rest = []
+            for bForce in bodyForces:
+                asm = getattr(self, "_b200_asm", None)
+                if asm is not None and hasattr(asm, "body_force_host") and len(bForce.elementSet) == len(self._b200_ex.elements) \
+                        and all(a is b for a, b in zip(bForce.elementSet, self._b200_ex.elements)):
+                    PExt += asm.body_force_host(np.asarray(bForce.getCurrentLoad(timeStep), dtype=float))
+                else:
+                    rest.append(bForce)
+            self.computationTimes["body forces"] += _time.time() - tic
+            if rest:
+                return super().computeBodyForces(rest, U_np, PExt, K, timeStep)
+            return PExt, K
+
         def assembleStiffnessCSR(self, K):
             tic = _time.time()
             KCsr = self.csrGenerator.updateCSR(K)  # whatever constraints wrote into the VIJ (elements left it zero)

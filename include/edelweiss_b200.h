@@ -121,6 +121,12 @@ int ewb_state_to_aos(const double* soa_dev, double* aos_dev, int64_t n_el, int n
  * zero the CSR rows of the given dofs and put 1 on their diagonal (pattern unchanged). */
 int ewb_apply_dirichlet_k(const ewb_plan* plan, double* csr_data_dev, const int32_t* dofs_dev, int64_t n, void* stream);
 
+/* ---- body force element loop: NIST.computeBodyForces (solvers/nonlinearimplicitstatic.py:516-557) with
+ * computeBodyForce of every element of the plan (elements/displacementelement/element.py:348-371, same in the TL element):
+ * PExt[el] += sum_gp outer(N[gp], load) detJ w.  The reference's N operator node ordering (xi/eta swapped relative to the
+ * derivative tables) is reproduced.  load_host: the current force vector (bodyforce.getCurrentLoad). */
+int ewb_body_force(ewb_plan* plan, const double* coords_dev, const double load_host[3], double* pext_dev, void* stream);
+
 /* ---- multi-GPU slab interface --------------------------------------------------------
  * Rank g owns the node planes [a_g, a_g+1) of a BoxGen box split along x; its local mesh also holds
  * the ghost plane a_g+1, whose partial CSR rows / P / F (contiguous tail of the local arrays) are sent

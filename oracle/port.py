@@ -414,6 +414,34 @@ def compute_tl_hyperelastic(eltype, material, props, X, Ue, dUe, stateRef):
     return Ke, Pe, state, np.zeros(state.shape[:2], dtype=bool)
 
 
+def shape_functions_bodyforce(nnodes: int, xi, eta, zeta):
+    """N[gp, a] as `computeNOperator` evaluates it (ref: displacementelement/_elementcomputationmatrices.py:106-212).
+    Its node table has xi and eta swapped relative to the derivative tables: node a sits at
+    (xi, eta, zeta) = (eta_a, xi_a, zeta_a) of the derivative convention.  Replicated, not "fixed"."""
+    xi, eta, zeta = (np.atleast_1d(np.asarray(v, dtype=float)) for v in (xi, eta, zeta))
+    lc = _local_coords(HEXA8_OFFSETS, 1) if nnodes == 8 else _local_coords(HEXA20_OFFSETS, 2)
+    a, b, c = lc[:, 1][None, :], lc[:, 0][None, :], lc[:, 2][None, :]  # swapped: a multiplies xi, b multiplies eta
+    X, E, Z = xi[:, None], eta[:, None], zeta[:, None]
+    fx, fe, fz = 1 + a * X, 1 + b * E, 1 + c * Z
+    if nnodes == 8:
+        return fx * fe * fz / 8
+    corner = fx * fe * fz * (a * X + b * E + c * Z - 2) / 8
+    return np.where(a == 0, (1 - X**2) * fe * fz / 4, np.where(b == 0, fx * (1 - E**2) * fz / 4, np.where(c == 0, fx * fe * (1 - Z**2) / 4, corner)))
+
+
+def body_force(eltype, coords, conn, load):
+    """PExt[el] += sum_gp outer(N[gp], load) detJ w for every element.
+    ref: elements/displacementelement/element.py:348-371 (computeBodyForce), solvers/nonlinearimplicitstatic.py:545-553."""
+    nn = ELEMENT_INFO[eltype.upper()]["nnodes"]
+    xi, eta, zeta, w = gauss_points(eltype.upper())
+    dN = shape_derivatives(nn, xi, eta, zeta)
+    N = shape_functions_bodyforce(nn, xi, eta, zeta)
+    detJ = np.linalg.det(jacobians(dN, coords[conn]))
+    Pe = np.einsum("ga,i,eg,g->eai", N, np.asarray(load, dtype=float), detJ, w).reshape(conn.shape[0], -1)
+    dofs = element_dofs(conn)
+    return np.bincount(dofs.reshape(-1), weights=Pe.reshape(-1), minlength=3 * coords.shape[0]), Pe
+
+
 def compute_elements(eltype, material, props, coords, conn, U, dU, stateRef, chunk=4096):
     """Batched element evaluation in element order; returns Ke, Pe, stateTemp, failed."""
     eltype = eltype.upper()

@@ -70,6 +70,14 @@ def make(name, elType, material, props, box, distort, scales, seed=0):
             k0, k1 = stateRef[..., 12], r["stateTemp"][..., 12]
             print(f"   {name} pass {p}: plastic GP fraction {(k1 > k0).mean():.3f}")
         m.accept()
+    # body force: the reference's own computeBodyForce on every element (element.py:348-371)
+    load = np.array([0.3, -0.000077, 1.7])
+    PExt = np.zeros(n)
+    for el, d in zip(m.elements, m.element_dofs()):
+        Pe = np.zeros(el.nDof)
+        el.computeBodyForce(Pe, np.zeros(el.nDof**2), load, np.zeros(el.nDof), np.array([0.0, 0.0]), 1.0)
+        PExt[d] += Pe
+    out.update(bodyforce_load=load, bodyforce_PExt=PExt)
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

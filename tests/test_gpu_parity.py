@@ -278,3 +278,18 @@ def test_sweep_edge_shapes(n, material, path):
     assert relerr(asm.P.cpu().numpy(), o["P"]) < TOL
     assert relerr(asm.F.cpu().numpy(), o["F"]) < TOL
     assert relerr(asm.state_aos("temp").cpu().numpy(), o["stateTemp"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_body_force_golden(name):
+    """ewb_body_force against the reference's computeBodyForce (incl. its xi/eta-swapped N operator)."""
+    g = load_golden(name)
+    asm = _assembly(g)
+    P = asm.body_force_host(g["bodyforce_load"])
+    assert relerr(P, g["bodyforce_PExt"]) < TOL
+    # accumulation semantics: PExt += ...
+    import torch
+
+    pext = torch.ones(asm.nDof, dtype=torch.float64, device=asm.device)
+    asm.body_force(g["bodyforce_load"], pext)
+    assert relerr(pext.cpu().numpy() - 1.0, g["bodyforce_PExt"]) < 1e-11

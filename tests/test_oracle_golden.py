@@ -85,3 +85,10 @@ def test_c_oracle_matches_reference_golden(name):
             V = np.ascontiguousarray(g[f"V{p}"])
             c.lib.ewo_update_csr(x.size, x.ctypes.data, V.ctypes.data, data.ctypes.data, data.size)
             assert np.array_equal(data, g[f"data{p}"])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_body_force(name):
+    g = load_golden(name)
+    P, _ = port.body_force(str(g["elType"]), g["coords"], g["conn"], g["bodyforce_load"])
+    assert relerr(P, g["bodyforce_PExt"]) < TOL

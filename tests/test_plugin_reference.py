@@ -41,6 +41,11 @@ class OracleBackend:
         self.out = o
         return o["P"], o["F"]
 
+    def body_force_host(self, load):
+        elType, material, props, coords, conn = self.args
+        self.body_force_calls = getattr(self, "body_force_calls", 0) + 1
+        return self.port.body_force(elType, coords, conn, load)[0]
+
     def csr_pattern_host(self):
         return self.out["indptr"], self.out["indices"]
 
@@ -99,6 +104,7 @@ def test_reference_jobs_through_plugin(testdir):
 def test_box_detection_and_state_views():
     U, model, created = _run_job("WallShearHexa8")
     assert created[0].box == (20, 20, 2)
+    assert created[0].body_force_calls > 0  # the job's *bodyforce went through the plugin's device hook
     el = next(iter(model.elements.values()))
     # getResultArray keeps returning live views of the accepted state (element.py:386-409)
     s = el.getResultArray("stress", 0)
