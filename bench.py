@@ -303,8 +303,10 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "elements_per_gpu": asm.nEl, "box_per_gpu": list(n), "nnz_per_gpu": asm.nnz, "dofs_per_gpu": asm.nDof,
                    "path": "fused-sweep" if fused else "generic-two-phase", "l2": "inputs+outputs (>3.6 GB/step) larger than the 126 MB L2",
-                   "partition": "x-slabs of %d element planes per GPU, ghost-plane rows sent to the upper neighbour (NCCL P2P), %d B per interface"
-                                % (n[0], slab.interface_bytes if slab is not None else 0) if world > 1 else "single GPU"},
+                   "partition": "x-slabs of %d element planes per GPU, ghost-plane rows %s, %d B per interface"
+                                % (n[0], "stored into the upper neighbour's memory by the sweep kernel (NVLink peer stores) + 4-byte status all-reduce"
+                                   if slab.exchange == "peer" else "sent to the upper neighbour (NCCL P2P)", slab.interface_bytes)
+                                if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.workload, "fused-sweep" if fused else "generic-two-phase"),
                      "peak_source": peak_src, "algorithmic_bytes_per_element": balg,
                      "kernel": "sweepKernel (1 launch = 1 step)" if fused else "computeElementsVij+gatherResidual+updateCsr (3 launches = 1 step)"},

@@ -70,6 +70,12 @@ SYMBOLS = {
     "ewb_apply_dirichlet_k": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "ewb_body_force": (C.c_int, [_P, _P, C.POINTER(C.c_double), _P, _P]),
     "ewb_interface_add": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "ewb_plan_set_peer": (C.c_int, [_P, _P, _P, _P]),
+    "ewb_plan_status_ptr": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "ewb_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "ewb_peer_free": (C.c_int, [_P]),
+    "ewb_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "ewb_peer_close": (C.c_int, [_P]),
     "ewb_launch_count": (C.c_int64, []),
 }
 

@@ -391,7 +391,7 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
     if (p->isBox && !(flags & EWB_FLAG_FORCE_GENERIC) && b->vij == nullptr) {
         int launches = 0;
         const char* pathEnv = getenv("EWB_PATH");  // "sweep" (fused) or "staged" (two streaming kernels)
-        const bool useStaged = (flags & EWB_FLAG_STAGED) || (pathEnv && std::string(pathEnv) == "staged");
+        const bool useStaged = ((flags & EWB_FLAG_STAGED) || (pathEnv && std::string(pathEnv) == "staged")) && !p->sweep.peerData;
         if (useStaged) {
             int rcS = p->staged.launch(p->elType, mc, p->nEl, p->nX, p->nY, p->nZ, p->conn, mp, b, p->failFlag, flags, st, &launches);
             g_launches += launches;
@@ -405,6 +405,7 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
     }
 
     // generic two-phase path
+    if (p->sweep.peerData) return fail(EWB_ERR_UNSUPPORTED, "ewb_assemble: peer interface buffers need the fused sweep path");
     const int nd = 3 * p->nn;
     if (!p->peScratch) CUDA_TRY(cudaMalloc((void**)&p->peScratch, (size_t)p->nEl * nd * sizeof(double)));
     double* V = nullptr;
@@ -487,6 +488,56 @@ int ewb_state_to_aos(const double* soa, double* aos, int64_t nEl, int nGp, int n
     const int64_t total = nEl * nGp * nState;
     stateTransposeKernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(soa, aos, nEl, nGp, nState, 0);
     LAUNCH_CHECK();
+    return EWB_OK;
+}
+
+int ewb_plan_set_peer(ewb_plan* p, double* peer_rows, double* peer_P, double* peer_F) {
+    if (!p) return fail(EWB_ERR_ARG, "ewb_plan_set_peer: null plan");
+    const bool any = peer_rows || peer_P || peer_F;
+    if (any && !(peer_rows && peer_P && peer_F)) return fail(EWB_ERR_ARG, "ewb_plan_set_peer: all three peer buffers or none");
+    if (any && !p->isBox) return fail(EWB_ERR_UNSUPPORTED, "ewb_plan_set_peer: structured (BoxGen) plans only");
+    p->sweep.peerData = peer_rows; p->sweep.peerP = peer_P; p->sweep.peerF = peer_F;
+    return EWB_OK;
+}
+
+int ewb_plan_status_ptr(ewb_plan* p, void** out) {
+    if (!p || !out) return fail(EWB_ERR_ARG, "ewb_plan_status_ptr: bad arguments");
+    *out = p->failFlag;
+    return EWB_OK;
+}
+
+int ewb_peer_alloc(int64_t bytes, void** ptr_out, unsigned char handle_out[EWB_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == EWB_IPC_HANDLE_BYTES, "IPC handle size");
+    if (bytes <= 0 || !ptr_out || !handle_out) return fail(EWB_ERR_ARG, "ewb_peer_alloc: bad arguments");
+    void* ptr = nullptr;
+    CUDA_TRY(cudaMalloc(&ptr, (size_t)bytes));
+    cudaError_t e = cudaMemset(ptr, 0, (size_t)bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) {
+        cudaFree(ptr);
+        return fail(EWB_ERR_CUDA, std::string("ewb_peer_alloc: ") + cudaGetErrorString(e));
+    }
+    std::memcpy(handle_out, &h, sizeof(h));
+    *ptr_out = ptr;
+    return EWB_OK;
+}
+
+int ewb_peer_free(void* ptr) {
+    if (ptr) CUDA_TRY(cudaFree(ptr));
+    return EWB_OK;
+}
+
+int ewb_peer_open(const unsigned char handle[EWB_IPC_HANDLE_BYTES], void** ptr_out) {
+    if (!handle || !ptr_out) return fail(EWB_ERR_ARG, "ewb_peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    CUDA_TRY(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return EWB_OK;
+}
+
+int ewb_peer_close(void* ptr) {
+    if (ptr) CUDA_TRY(cudaIpcCloseMemHandle(ptr));
     return EWB_OK;
 }
 

@@ -42,6 +42,11 @@ struct SweepArgs {
     int wantK;
     int accumulatePF;
     int spinNs;  // back-off of the flag polling loops (tuning knob, EWB_SPIN_NS)
+    // Slab interface (multi-GPU): when set, the rows / P / F of the LAST node plane (the ghost plane owned by the upper
+    // neighbour) are stored straight into that neighbour's receive buffers over NVLink instead of the local tail.
+    double* peerData;
+    double* peerP;
+    double* peerF;
     long long* timing;  // optional [gridDim][NW][12] cycle counters (EWB_TIMING builds only)
 };
 
@@ -572,7 +577,8 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
     // flush the finished segments (nullptr = not finished) of this warp's owned nodes of plane ix, clear them
     auto flushPlane = [&](int ix, double* sM, double* s0, double* sP, double* pf) {
         const int cx = (ix > 0) + 1 + (ix < NX - 1);
-        double* xbase = A.data + 9 * (int64_t)pre(ix) * totYZ;
+        const bool toPeer = A.peerData != nullptr && ix == NX - 1;  // ghost plane -> upper neighbour's receive buffer
+        double* xbase = toPeer ? A.peerData : A.data + 9 * (int64_t)pre(ix) * totYZ;
         const int rx0 = ix > 0 ? 1 : 0;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
@@ -610,7 +616,11 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
                 pf[col * 6 + 3 + lane] = 0.0;
                 const int ly = 2 * pyq + (cc >> 1), lz = 2 * pzq + (cc & 1);
                 const int64_t dof = 3 * ((((int64_t)ix * NY + (y0 + ly)) * NZ) + (z0 + lz)) + lane;
-                if (A.accumulatePF) {
+                if (toPeer) {
+                    const int64_t pd = dof - 3 * (int64_t)ix * NY * NZ;
+                    A.peerP[pd] = pv;
+                    A.peerF[pd] = fv;
+                } else if (A.accumulatePF) {
                     A.P[dof] += pv;
                     A.F[dof] += fv;
                 } else {
@@ -989,7 +999,8 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
     // flush the finished segments (nullptr = not finished) of this warp's owned nodes of plane ix, clear them
     auto flushPlane = [&](int ix, double* sM, double* s0, double* sP, double* pf) {
         const int cx = (ix > 0) + 1 + (ix < NX - 1);
-        double* xbase = A.data + 9 * (int64_t)pre(ix) * totYZ;
+        const bool toPeer = A.peerData != nullptr && ix == NX - 1;  // ghost plane -> upper neighbour's receive buffer
+        double* xbase = toPeer ? A.peerData : A.data + 9 * (int64_t)pre(ix) * totYZ;
         const int rx0 = ix > 0 ? 1 : 0;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
@@ -1027,7 +1038,11 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
                 pf[col * 6 + 3 + lane] = 0.0;
                 const int ly = 2 * pyq + (cc >> 1), lz = 2 * pzq + (cc & 1);
                 const int64_t dof = 3 * ((((int64_t)ix * NY + (y0 + ly)) * NZ) + (z0 + lz)) + lane;
-                if (A.accumulatePF) {
+                if (toPeer) {
+                    const int64_t pd = dof - 3 * (int64_t)ix * NY * NZ;
+                    A.peerP[pd] = pv;
+                    A.peerF[pd] = fv;
+                } else if (A.accumulatePF) {
                     A.P[dof] += pv;
                     A.F[dof] += fv;
                 } else {
@@ -1171,6 +1186,9 @@ struct SweepPlan {
         return 0;
     }
     void release() {}
+    double* peerData = nullptr;  // set by ewb_plan_set_peer
+    double* peerP = nullptr;
+    double* peerF = nullptr;
 
     template <int TY, int TZ>
     int fillArgs(SweepArgs& a, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st, int NW_) {
@@ -1208,6 +1226,7 @@ struct SweepPlan {
         a.data = b->csr_data; a.P = b->P; a.F = b->F; a.mp = mp; a.failFlag = failFlag;
         a.wantK = (flags & EWB_FLAG_NO_STIFFNESS) ? 0 : 1;
         a.accumulatePF = (flags & EWB_FLAG_ACCUMULATE_PF) ? 1 : 0;
+        a.peerData = peerData; a.peerP = peerP; a.peerF = peerF;
         return EWB_OK;
     }
 

@@ -6,9 +6,14 @@ element planes [a_g, a_g+1) and node planes [a_g, a_g+1) (the last rank also the
 mesh holds one more node plane — the ghost plane a_g+1 owned by rank g+1 — whose partial rows are the
 contiguous TAIL of the local CSR value array (and of P, F).  One neighbour exchange per assembly:
 
-    rank g  --(tail of csr_data, P, F)-->  rank g+1   (torch.distributed P2P: NCCL over NVLink on GPUs)
+    rank g  --(tail of csr_data, P, F)-->  rank g+1
 
-then `ewb_interface_add` adds the dx=0 half of the received rows onto the receiver's first node plane
+On GPUs the transfer is fused into the sweep kernel ("peer" exchange, the default): the CTAs that finish ghost-plane rows
+store them straight into rank g+1's receive buffer (CUDA-IPC mapped peer memory, NVLink) while the rest of the slab is
+still being computed; the only collective is a 4-byte max-all-reduce of the status words, which orders the receiver's
+interface add after the sender's kernel and gives every rank the same cut-back decision.  The "nccl" exchange (send/recv
+of the finished tail, torch.distributed P2P) is the fallback when peer mapping is not available, and what the CPU tests
+run over gloo.  Then `ewb_interface_add` adds the dx=0 half of the received rows onto the receiver's first node plane
 (own contribution first, neighbour second: deterministic).  The dx=-1 half of the received rows is the
 receiver's lower halo block.  No all-reduce is needed for K.
 
@@ -93,10 +98,22 @@ def exchange_tails(layout: SlabLayout, data, P, F, recv, recvP, recvF, indptr_ho
             r.wait()
 
 
-class SlabAssembly:
-    """One rank's share of a distributed BoxGen assembly: local ElementAssembly + interface exchange."""
+class _RawDeviceArray:
+    """__cuda_array_interface__ view of a raw device allocation (so torch can wrap it without owning it)."""
 
-    def __init__(self, n, lengths, elType, material, props, rank, world, device):
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+class SlabAssembly:
+    """One rank's share of a distributed BoxGen assembly: local ElementAssembly + interface exchange.
+
+    exchange: "peer" (ghost-plane rows stored into the neighbour's memory by the sweep kernel), "nccl" (send/recv of the
+    finished tail) or None = $EWB_EXCHANGE, default "peer" with a collective fallback to "nccl"."""
+
+    def __init__(self, n, lengths, elType, material, props, rank, world, device, exchange=None, group=None):
+        import os
+
         import torch
 
         from .assembly import ElementAssembly
@@ -112,7 +129,75 @@ class SlabAssembly:
         self.recv = torch.zeros(head if lay.has_lower else 1, **f64)
         self.recvP = torch.zeros(lay.planeDofs if lay.has_lower else 1, **f64)
         self.recvF = torch.zeros(lay.planeDofs if lay.has_lower else 1, **f64)
-        self.interface_bytes = 8 * (head + 2 * lay.planeDofs) if lay.has_lower else 0
+        self.interface_bytes = 8 * (head + 2 * lay.planeDofs) if world > 1 else 0
+        self.step = 0
+        self._own = self._peer = None
+        self.exchange = (exchange or os.environ.get("EWB_EXCHANGE", "peer")) if world > 1 else "none"
+        if self.exchange not in ("peer", "nccl", "none"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        if self.exchange == "peer":
+            self._setup_peer(head, group)
+
+    # ---- fused transfer: the upper neighbour's receive buffers mapped into this process ----------------------------
+    def _setup_peer(self, head, group):
+        import warnings
+
+        import torch
+        import torch.distributed as dist
+
+        from ._lib import check
+
+        a, lay = self.asm, self.layout
+        seg = head + 2 * lay.planeDofs  # doubles per parity: [rows | P | F]
+        handle, err = None, None
+        try:
+            if lay.has_lower:
+                ptr, h = C.c_void_p(), C.create_string_buffer(64)
+                check(a.lib.ewb_peer_alloc(2 * seg * 8, C.byref(ptr), h))
+                self._own, handle = ptr.value, h.raw
+        except Exception as e:  # noqa: BLE001 - any failure -> collective fallback below
+            err = e
+        handles = [None] * lay.world
+        dist.all_gather_object(handles, handle, group=group)
+        try:
+            if err is None and lay.has_upper:
+                if handles[lay.rank + 1] is None:
+                    raise RuntimeError("upper neighbour has no receive buffer")
+                ptr = C.c_void_p()
+                check(a.lib.ewb_peer_open(handles[lay.rank + 1], C.byref(ptr)))
+                self._peer = ptr.value
+                upHead = self._peer_head = int(self.indptr_host[-1]) - lay.tail_start(self.indptr_host)
+                self._peer_seg = upHead + 2 * lay.planeDofs
+        except Exception as e:  # noqa: BLE001
+            err = e
+        oks = [None] * lay.world
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks):
+            if err is not None:
+                warnings.warn(f"peer exchange unavailable on rank {lay.rank} ({err}); using the NCCL send/recv exchange")
+            self.close()
+            self.exchange = "nccl"
+            return
+        st = C.c_void_p()
+        check(a.lib.ewb_plan_status_ptr(a.plan, C.byref(st)))
+        self.status = torch.as_tensor(_RawDeviceArray(st.value, 1, "<i4"), device=a.device)
+        self._views = []
+        if lay.has_lower:
+            whole = torch.as_tensor(_RawDeviceArray(self._own, 2 * seg, "<f8"), device=a.device)
+            for par in range(2):
+                b = whole[par * seg : (par + 1) * seg]
+                self._views.append((b[:head], b[head : head + lay.planeDofs], b[head + lay.planeDofs :]))
+
+    def close(self):
+        """Unmap / free the peer buffers (safe to call twice)."""
+        lib = self.asm.lib
+        if self._peer:
+            lib.ewb_plan_set_peer(self.asm.plan, None, None, None)
+            lib.ewb_peer_close(C.c_void_p(self._peer))
+            self._peer = None
+        if self._own:
+            lib.ewb_peer_free(C.c_void_p(self._own))
+            self._own = None
 
     def assemble(self, flags=0, group=None):
         """Local fused assembly, then the neighbour exchange and the interface add (all on the current stream)."""
@@ -121,13 +206,26 @@ class SlabAssembly:
         from ._lib import check
 
         a, lay = self.asm, self.layout
-        a.assemble(flags)
-        if lay.world > 1:
-            exchange_tails(lay, a.csr_data, a.P, a.F, self.recv, self.recvP, self.recvF, self.indptr_host, dist, group)
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        if self.exchange == "peer":
+            par = self.step & 1  # receive buffers are double buffered: a fast sender may already be one assembly ahead
+            if lay.has_upper:
+                base = self._peer + 8 * par * self._peer_seg
+                check(a.lib.ewb_plan_set_peer(a.plan, C.c_void_p(base), C.c_void_p(base + 8 * self._peer_head),
+                                              C.c_void_p(base + 8 * (self._peer_head + lay.planeDofs))))
+            a.assemble(flags)
+            # orders the neighbour's peer stores before the interface add; every rank sees the same cut-back request
+            dist.all_reduce(self.status, op=dist.ReduceOp.MAX, group=group)
             if lay.has_lower:
-                p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-                check(a.lib.ewb_interface_add(p(self.indptr), lay.planeDofs, p(a.csr_data), p(self.recv), p(a.P), p(a.F), p(self.recvP), p(self.recvF),
-                                              a._stream()))
+                self.recv, self.recvP, self.recvF = self._views[par]
+        else:
+            a.assemble(flags)
+            if lay.world > 1:
+                exchange_tails(lay, a.csr_data, a.P, a.F, self.recv, self.recvP, self.recvF, self.indptr_host, dist, group)
+        if lay.has_lower:
+            check(a.lib.ewb_interface_add(p(self.indptr), lay.planeDofs, p(a.csr_data), p(self.recv), p(a.P), p(a.F), p(self.recvP), p(self.recvF),
+                                          a._stream()))
+        self.step += 1
 
     # owned part of the distributed system (rows of owned dofs, local column numbering + lower halo block in self.recv)
     def owned_slices(self):

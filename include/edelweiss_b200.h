@@ -138,6 +138,25 @@ int ewb_body_force(ewb_plan* plan, const double* coords_dev, const double load_h
 int ewb_interface_add(const int32_t* indptr_dev, int64_t n_rows, double* csr_data_dev, const double* recv_rows_dev, double* P_dev,
                       double* F_dev, const double* recv_P_dev, const double* recv_F_dev, void* stream);
 
+/* Fused interface transfer: with peer buffers set, ewb_assemble's sweep kernel stores the ghost plane's rows / P / F
+ * straight into the upper neighbour's receive buffers (peer memory over NVLink) while the rest of the slab is still being
+ * computed, instead of into the local tail; no send afterwards.  The receiver orders its ewb_interface_add after the
+ * sender's kernel with one small collective (the all-reduce of the status words, below).  Pass NULLs to switch back to
+ * the local tail.  Structured (BoxGen) plans only. */
+int ewb_plan_set_peer(ewb_plan* plan, double* peer_rows_dev, double* peer_P_dev, double* peer_F_dev);
+
+/* Device address of the plan's status word (int32; bit 0 = cutback requested, see ewb_poll_status): a distributed caller
+ * max-reduces it across ranks so that every rank takes the same cut-back decision (nonlinearimplicitstatic.py:253-262). */
+int ewb_plan_status_ptr(ewb_plan* plan, void** status_dev_out);
+
+/* Receive buffers reachable from another process' GPU (CUDA IPC).  ewb_peer_alloc: device allocation + 64-byte handle to
+ * pass to the neighbour process; ewb_peer_open maps a neighbour's handle into this process (peer access enabled). */
+#define EWB_IPC_HANDLE_BYTES 64
+int ewb_peer_alloc(int64_t bytes, void** ptr_out, unsigned char handle_out[EWB_IPC_HANDLE_BYTES]);
+int ewb_peer_free(void* ptr);
+int ewb_peer_open(const unsigned char handle[EWB_IPC_HANDLE_BYTES], void** ptr_out);
+int ewb_peer_close(void* ptr);
+
 /* number of this library's kernel launches since load (bench.py's gpu_launches) */
 int64_t ewb_launch_count(void);
 

@@ -29,7 +29,7 @@ def _inputs():
     return coords, conn, dU
 
 
-def _worker(rank, world, port_no, q):
+def _worker(rank, world, port_no, q, exchange):
     import torch
     import torch.distributed as dist
 
@@ -41,23 +41,27 @@ def _worker(rank, world, port_no, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         coords, conn, dU = _inputs()
-        slab = SlabAssembly(N, (9.0, 8.0, 7.0), "C3D8", "vonmises", PROPS, rank, world, torch.device("cuda", rank))
+        slab = SlabAssembly(N, (9.0, 8.0, 7.0), "C3D8", "vonmises", PROPS, rank, world, torch.device("cuda", rank), exchange=exchange)
+        assert slab.exchange == exchange, "requested exchange mode is not available: %s" % slab.exchange
         lay, asm = slab.layout, slab.asm
         n0 = lay.node_offset()
         asm.coords.copy_(torch.as_tensor(coords[n0 : n0 + lay.nNodeLoc]))
         ldU = dU[3 * n0 : 3 * (n0 + lay.nNodeLoc)]
         asm.U.copy_(torch.as_tensor(ldU))
         asm.dU.copy_(torch.as_tensor(ldU))
-        slab.assemble()
+        for _ in range(3):  # repeated assemblies: the double-buffered receive side must stay consistent
+            slab.assemble()
         asm.poll()
         rows, nnzs = slab.owned_slices()
         q.put((rank, 3 * n0, slab.indptr_host[: lay.ownedDofs + 1].copy(), slab.indices.cpu().numpy()[nnzs], asm.csr_data.cpu().numpy()[nnzs],
                asm.P.cpu().numpy()[rows], asm.F.cpu().numpy()[rows], slab.recv.cpu().numpy(), lay.planeDofs, lay.has_lower))
+        slab.close()
     finally:
         dist.destroy_process_group()
 
 
-def test_two_gpu_slabs_match_single_gpu():
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_two_gpu_slabs_match_single_gpu(exchange):
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -71,13 +75,18 @@ def test_two_gpu_slabs_match_single_gpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port_no = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port_no, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port_no, q, exchange)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=300) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        results = [q.get(timeout=240) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:  # never leave a rank behind in a collective
+            if p.is_alive():
+                p.kill()
     coords, conn, dU = _inputs()
     ref = ElementAssembly("C3D8", conn, coords, "vonmises", PROPS, box=N)
     ref.U.copy_(torch.as_tensor(dU))
