@@ -466,12 +466,14 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
     constexpr bool COMPUTE_FIRST = NW <= 12;  // >= 168 registers per thread available
 
     extern __shared__ double smem[];
-    double* seg0a = smem + AL::OFF_0A;  // dx=0 segment, ping
-    double* seg0b = smem + AL::OFF_0B;  // dx=0 segment, pong
-    double* segP = smem + AL::OFF_P;    // lower plane, dx=+1
-    double* segM = smem + AL::OFF_M;    // upper plane, dx=-1
-    double* pfA = smem + AL::PF;        // [NCOL][6] P,F of the lower plane
-    double* pfB = pfA + NCOL * 6;       // upper plane
+    // Accumulator segments are addressed by OFFSETS (doubles) into `smem`, never by pointers that get swapped or selected:
+    // a selected pointer loses its address space and the accumulation degrades to generic LD/ST with 64-bit address math.
+    constexpr int seg0a = AL::OFF_0A;  // dx=0 segment, ping
+    constexpr int seg0b = AL::OFF_0B;  // dx=0 segment, pong
+    constexpr int segP = AL::OFF_P;    // lower plane, dx=+1
+    constexpr int segM = AL::OFF_M;    // upper plane, dx=-1
+    constexpr int pfA = AL::PF;        // [NCOL][6] P,F of the lower plane
+    constexpr int pfB = pfA + NCOL * 6;  // upper plane
     int* colPart = reinterpret_cast<int*>(smem + AL::INFO);
     int* colCycz = colPart + NCOL;
     int* laneOff = colCycz + NCOL;                // [NCOL][32]
@@ -516,10 +518,10 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
     }
     __syncthreads();  // the only CTA-wide barrier: from here on the warps are ordered by dataflow flags
 
-    double* lo0 = seg0a;
-    double* hi0 = seg0b;
-    double* pfLo = pfA;
-    double* pfHi = pfB;
+    int lo0 = seg0a;
+    int hi0 = seg0b;
+    int pfLo = pfA;
+    int pfHi = pfB;
     const int64_t cstride = (int64_t)A.nX * A.nY * A.nZ * 8;
     const double* __restrict__ uSrc = TL ? A.U : A.dU;
     const int64_t totYZ = (int64_t)totY * totZ;
@@ -575,7 +577,7 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
     const bool aHi = ndx(na) != 0;
 
     // flush the finished segments (nullptr = not finished) of this warp's owned nodes of plane ix, clear them
-    auto flushPlane = [&](int ix, double* sM, double* s0, double* sP, double* pf) {
+    auto flushPlane = [&](int ix, int sM, int s0, int sP, int pf) {  // segment offsets, -1 = not finished
         const int cx = (ix > 0) + 1 + (ix < NX - 1);
         const bool toPeer = A.peerData != nullptr && ix == NX - 1;  // ghost plane -> upper neighbour's receive buffer
         double* xbase = toPeer ? A.peerData : A.data + 9 * (int64_t)pre(ix) * totYZ;
@@ -593,11 +595,11 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
             if (A.wantK && lane < 27) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                    double* seg = d == 0 ? sM : (d == 1 ? s0 : sP);
-                    if (seg == nullptr) continue;
+                    const int seg = d == 0 ? sM : (d == 1 ? s0 : sP);
+                    if (seg < 0) continue;
                     const int dx = d - 1;
                     const bool ok = ix + dx >= 0 && ix + dx < NX && lo >= 0;
-                    double* src = seg + col * CS + lane;
+                    double* src = smem + (seg + col * CS + lane);
                     double* dst = rowBase + 3 * ((dx + rx0) * cycz);
                     const double v0 = src[0], v1 = src[27], v2 = src[54];
                     src[0] = 0.0;
@@ -610,10 +612,11 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
                     }
                 }
             }
-            if (pf != nullptr && lane < 3) {
-                const double pv = pf[col * 6 + lane], fv = pf[col * 6 + 3 + lane];
-                pf[col * 6 + lane] = 0.0;
-                pf[col * 6 + 3 + lane] = 0.0;
+            if (pf >= 0 && lane < 3) {
+                double* pfp = smem + (pf + col * 6 + lane);
+                const double pv = pfp[0], fv = pfp[3];
+                pfp[0] = 0.0;
+                pfp[3] = 0.0;
                 const int ly = 2 * pyq + (cc >> 1), lz = 2 * pzq + (cc & 1);
                 const int64_t dof = 3 * ((((int64_t)ix * NY + (y0 + ly)) * NZ) + (z0 + lz)) + lane;
                 if (toPeer) {
@@ -714,10 +717,10 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
             statePrefetch(ex + 1);
         }
         // per-step accumulation bases of this lane (segments rotate every plane)
-        double* accBase[2];
+        int accBase[2];
 #pragma unroll
         for (int t = 0; t < 2; ++t) accBase[t] = (aHi ? (accSame[t] ? hi0 : segM) : (accSame[t] ? lo0 : segP)) + accOff[t];
-        double* pfBase = (aHi ? pfHi : pfLo) + (ndy(na) * TZ + ndz(na)) * 6;
+        const int pfBase = (aHi ? pfHi : pfLo) + (ndy(na) * TZ + ndz(na)) * 6;
         const bool planeOwned = aHi ? hiOwned : loOwned;
         // ------------- phase B: 4 colour rounds, one element per round -------------
 #pragma unroll 1
@@ -740,7 +743,7 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
                 if (planeOwned && ((ownMask >> k) & 1)) {
                     const int eOff = eOff0 + (k >> 1) * TZ + (k & 1);
                     if (bq == 0) {
-                        double* pf = pfBase + eOff * 6;
+                        double* pf = smem + (pfBase + eOff * 6);
 #pragma unroll
                         for (int i = 0; i < 3; ++i) {
                             pf[i] += Pr[i];
@@ -750,7 +753,7 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
                     if (A.wantK) {
 #pragma unroll
                         for (int t = 0; t < 2; ++t) {
-                            double* dst = accBase[t] + eOff * CS;
+                            double* dst = smem + (accBase[t] + eOff * CS);
                             const double* Kt = t ? K1 : K0;
 #pragma unroll
                             for (int i = 0; i < 3; ++i)
@@ -774,16 +777,16 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
         waitFlags(doneCnt, depD, hasD, 4 * (step + 1), A.failFlag, A.spinNs);
         EWB_ACC(4, tWF);
         EWB_TIC(tF);
-        if (loOwned) flushPlane(ex, nullptr, lo0, segP, pfLo);
-        if (hiOwned) flushPlane(ex + 1, segM, nullptr, nullptr, nullptr);
-        if (ex == exEnd && xb == NX) flushPlane(NX - 1, nullptr, hi0, nullptr, pfHi);  // last node plane: nothing above it
+        if (loOwned) flushPlane(ex, -1, lo0, segP, pfLo);
+        if (hiOwned) flushPlane(ex + 1, segM, -1, -1, -1);
+        if (ex == exEnd && xb == NX) flushPlane(NX - 1, -1, hi0, -1, pfHi);  // last node plane: nothing above it
         EWB_SMEM_FENCE();
         __syncwarp();
         if (lane == 0) flushedCnt[p] = step + 1;
         EWB_ACC(5, tF);
         {
-            double* t0 = lo0; lo0 = hi0; hi0 = t0;
-            double* t1 = pfLo; pfLo = pfHi; pfHi = t1;
+            const int t0 = lo0; lo0 = hi0; hi0 = t0;
+            const int t1 = pfLo; pfLo = pfHi; pfHi = t1;
         }
     }
 #ifdef EWB_TIMING
@@ -801,7 +804,8 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
 // plane step ahead into double-buffered Gauss-point records.  The latency-bound phase A thereby overlaps the FP64- and
 // shared-memory-bound consumer work instead of preceding it.
 template <int MC, bool TL, int TY, int TZ, int NWP>
-__global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 1) sweepKernelPC(const SweepArgs A) {
+__global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, ((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) <= 8 ? 2 : 1))
+    sweepKernelPC(const SweepArgs A) {
     using R = RecLayout<MC>;
     using AL = AccLayout<TY, TZ>;
     constexpr int NPY = (TY + 1) / 2, NPZ = (TZ + 1) / 2, NW = NPY * NPZ;
@@ -813,12 +817,14 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
     constexpr bool COMPUTE_FIRST = (NW + NWP) <= 12;
 
     extern __shared__ double smem[];
-    double* seg0a = smem + AL::OFF_0A;  // dx=0 segment, ping
-    double* seg0b = smem + AL::OFF_0B;  // dx=0 segment, pong
-    double* segP = smem + AL::OFF_P;    // lower plane, dx=+1
-    double* segM = smem + AL::OFF_M;    // upper plane, dx=-1
-    double* pfA = smem + AL::PF;        // [NCOL][6] P,F of the lower plane
-    double* pfB = pfA + NCOL * 6;       // upper plane
+    // Accumulator segments are addressed by OFFSETS (doubles) into `smem`, never by pointers that get swapped or selected:
+    // a selected pointer loses its address space and the accumulation degrades to generic LD/ST with 64-bit address math.
+    constexpr int seg0a = AL::OFF_0A;  // dx=0 segment, ping
+    constexpr int seg0b = AL::OFF_0B;  // dx=0 segment, pong
+    constexpr int segP = AL::OFF_P;    // lower plane, dx=+1
+    constexpr int segM = AL::OFF_M;    // upper plane, dx=-1
+    constexpr int pfA = AL::PF;        // [NCOL][6] P,F of the lower plane
+    constexpr int pfB = pfA + NCOL * 6;  // upper plane
     int* colPart = reinterpret_cast<int*>(smem + AL::INFO);
     int* colCycz = colPart + NCOL;
     int* laneOff = colCycz + NCOL;                // [NCOL][32]
@@ -865,10 +871,10 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
     }
     __syncthreads();  // the only CTA-wide barrier: from here on the warps are ordered by dataflow flags
 
-    double* lo0 = seg0a;
-    double* hi0 = seg0b;
-    double* pfLo = pfA;
-    double* pfHi = pfB;
+    int lo0 = seg0a;
+    int hi0 = seg0b;
+    int pfLo = pfA;
+    int pfHi = pfB;
     const int64_t cstride = (int64_t)A.nX * A.nY * A.nZ * 8;
     const double* __restrict__ uSrc = TL ? A.U : A.dU;
     const int64_t totYZ = (int64_t)totY * totZ;
@@ -997,7 +1003,7 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
     const bool aHi = ndx(na) != 0;
 
     // flush the finished segments (nullptr = not finished) of this warp's owned nodes of plane ix, clear them
-    auto flushPlane = [&](int ix, double* sM, double* s0, double* sP, double* pf) {
+    auto flushPlane = [&](int ix, int sM, int s0, int sP, int pf) {  // segment offsets, -1 = not finished
         const int cx = (ix > 0) + 1 + (ix < NX - 1);
         const bool toPeer = A.peerData != nullptr && ix == NX - 1;  // ghost plane -> upper neighbour's receive buffer
         double* xbase = toPeer ? A.peerData : A.data + 9 * (int64_t)pre(ix) * totYZ;
@@ -1015,11 +1021,11 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
             if (A.wantK && lane < 27) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                    double* seg = d == 0 ? sM : (d == 1 ? s0 : sP);
-                    if (seg == nullptr) continue;
+                    const int seg = d == 0 ? sM : (d == 1 ? s0 : sP);
+                    if (seg < 0) continue;
                     const int dx = d - 1;
                     const bool ok = ix + dx >= 0 && ix + dx < NX && lo >= 0;
-                    double* src = seg + col * CS + lane;
+                    double* src = smem + (seg + col * CS + lane);
                     double* dst = rowBase + 3 * ((dx + rx0) * cycz);
                     const double v0 = src[0], v1 = src[27], v2 = src[54];
                     src[0] = 0.0;
@@ -1032,10 +1038,11 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
                     }
                 }
             }
-            if (pf != nullptr && lane < 3) {
-                const double pv = pf[col * 6 + lane], fv = pf[col * 6 + 3 + lane];
-                pf[col * 6 + lane] = 0.0;
-                pf[col * 6 + 3 + lane] = 0.0;
+            if (pf >= 0 && lane < 3) {
+                double* pfp = smem + (pf + col * 6 + lane);
+                const double pv = pfp[0], fv = pfp[3];
+                pfp[0] = 0.0;
+                pfp[3] = 0.0;
                 const int ly = 2 * pyq + (cc >> 1), lz = 2 * pzq + (cc & 1);
                 const int64_t dof = 3 * ((((int64_t)ix * NY + (y0 + ly)) * NZ) + (z0 + lz)) + lane;
                 if (toPeer) {
@@ -1079,10 +1086,10 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
         EWB_ACC(0, tWP);
         const double* wt = tables + (size_t)((step & 1) * NW + p) * 4 * R::PER_EL;
         // per-step accumulation bases of this lane (segments rotate every plane)
-        double* accBase[2];
+        int accBase[2];
 #pragma unroll
         for (int t = 0; t < 2; ++t) accBase[t] = (aHi ? (accSame[t] ? hi0 : segM) : (accSame[t] ? lo0 : segP)) + accOff[t];
-        double* pfBase = (aHi ? pfHi : pfLo) + (ndy(na) * TZ + ndz(na)) * 6;
+        const int pfBase = (aHi ? pfHi : pfLo) + (ndy(na) * TZ + ndz(na)) * 6;
         const bool planeOwned = aHi ? hiOwned : loOwned;
         // ------------- phase B: 4 colour rounds, one element per round -------------
 #pragma unroll 1
@@ -1116,7 +1123,7 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
                 if (planeOwned && ((ownMask >> k) & 1)) {
                     const int eOff = eOff0 + (k >> 1) * TZ + (k & 1);
                     if (bq == 0) {
-                        double* pf = pfBase + eOff * 6;
+                        double* pf = smem + (pfBase + eOff * 6);
 #pragma unroll
                         for (int i = 0; i < 3; ++i) {
                             pf[i] += Pr[i];
@@ -1126,7 +1133,7 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
                     if (A.wantK) {
 #pragma unroll
                         for (int t = 0; t < 2; ++t) {
-                            double* dst = accBase[t] + eOff * CS;
+                            double* dst = smem + (accBase[t] + eOff * CS);
                             double Kf[9];
                             if (!COMPUTE_FIRST) finishBlock<MC>(tacc_, t, A.mp, Kf);
                             const double* Kt = COMPUTE_FIRST ? (t ? K1 : K0) : Kf;
@@ -1148,16 +1155,16 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
         waitFlags(doneCnt, depD, hasD, 4 * (step + 1), A.failFlag, A.spinNs);
         EWB_ACC(4, tWF);
         EWB_TIC(tF);
-        if (loOwned) flushPlane(ex, nullptr, lo0, segP, pfLo);
-        if (hiOwned) flushPlane(ex + 1, segM, nullptr, nullptr, nullptr);
-        if (ex == exEnd && xb == NX) flushPlane(NX - 1, nullptr, hi0, nullptr, pfHi);  // last node plane: nothing above it
+        if (loOwned) flushPlane(ex, -1, lo0, segP, pfLo);
+        if (hiOwned) flushPlane(ex + 1, segM, -1, -1, -1);
+        if (ex == exEnd && xb == NX) flushPlane(NX - 1, -1, hi0, -1, pfHi);  // last node plane: nothing above it
         EWB_SMEM_FENCE();
         __syncwarp();
         if (lane == 0) flushedCnt[p] = step + 1;
         EWB_ACC(5, tF);
         {
-            double* t0 = lo0; lo0 = hi0; hi0 = t0;
-            double* t1 = pfLo; pfLo = pfHi; pfHi = t1;
+            const int t0 = lo0; lo0 = hi0; hi0 = t0;
+            const int t1 = pfLo; pfLo = pfHi; pfHi = t1;
         }
     }
 #ifdef EWB_TIMING
@@ -1275,6 +1282,10 @@ struct SweepPlan {
             else if (tile == 753) rc = launchPC<MC_LE, false, 7, 5, 3>(mp, b, failFlag, flags, st);
             else if (tile == 752) rc = launchPC<MC_LE, false, 7, 5, 2>(mp, b, failFlag, flags, st);
             else if (tile == 75) rc = launchT<MC_LE, false, 7, 5>(mp, b, failFlag, flags, st);
+            else if (tile == 532) rc = launchPC<MC_LE, false, 5, 3, 2>(mp, b, failFlag, flags, st);
+            else if (tile == 352) rc = launchPC<MC_LE, false, 3, 5, 2>(mp, b, failFlag, flags, st);
+            else if (tile == 734) rc = launchPC<MC_LE, false, 7, 3, 4>(mp, b, failFlag, flags, st);
+            else if (tile == 553) rc = launchPC<MC_LE, false, 5, 5, 3>(mp, b, failFlag, flags, st);
             else rc = launchPC<MC_LE, false, 7, 5, 4>(mp, b, failFlag, flags, st);
         }
         else if (elType == EWB_C3D8 && mc == MC_VM) rc = launchT<MC_VM, false, 7, 5>(mp, b, failFlag, flags, st);

@@ -26,7 +26,7 @@ asm.poll()
 lib = asm.lib
 lib.ewb_debug_timing.restype = C.c_int64
 lib.ewb_debug_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
-NW = 12
+NW = int(os.environ.get("EWB_NW", "12"))
 buf = np.zeros(225 * 64 * NW * 12, dtype=np.int64)
 m = lib.ewb_debug_timing(asm.plan, buf.ctypes.data, buf.size)
 t = buf[:m].reshape(-1, NW, 12)
