@@ -1272,7 +1272,7 @@ struct SweepPlan {
     int launch(int elType, int mc, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st, int* launches) {
         int rc = EWB_ERR_UNSUPPORTED;
         const char* tileEnv = getenv("EWB_TILE");
-        const int tile = tileEnv ? atoi(tileEnv) : 754;  // default: producer/consumer kernel, 7x5 tile, 4 producer warps
+        const int tile = tileEnv ? atoi(tileEnv) : 553;  // default: producer/consumer kernel, 5x5 tile, 9 consumer + 3 producer warps
         if (elType == EWB_C3D8 && mc == MC_LE) {
             if (tile == 77) rc = launchT<MC_LE, false, 7, 7>(mp, b, failFlag, flags, st);
             else if (tile == 55) rc = launchT<MC_LE, false, 5, 5>(mp, b, failFlag, flags, st);
@@ -1286,7 +1286,7 @@ struct SweepPlan {
             else if (tile == 352) rc = launchPC<MC_LE, false, 3, 5, 2>(mp, b, failFlag, flags, st);
             else if (tile == 734) rc = launchPC<MC_LE, false, 7, 3, 4>(mp, b, failFlag, flags, st);
             else if (tile == 553) rc = launchPC<MC_LE, false, 5, 5, 3>(mp, b, failFlag, flags, st);
-            else rc = launchPC<MC_LE, false, 7, 5, 4>(mp, b, failFlag, flags, st);
+            else rc = launchPC<MC_LE, false, 5, 5, 3>(mp, b, failFlag, flags, st);
         }
         else if (elType == EWB_C3D8 && mc == MC_VM) rc = launchT<MC_VM, false, 7, 5>(mp, b, failFlag, flags, st);
         else if (elType == EWB_C3D8TL && mc == MC_NH) rc = launchT<MC_NH, true, 7, 5>(mp, b, failFlag, flags, st);
