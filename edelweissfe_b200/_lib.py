@@ -10,14 +10,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EWB_LIB_PATH", os.path.join(_HERE, "libedelweiss_b200.so"))  # override: experiments only
 
 # enums of include/edelweiss_b200.h
-EWB_C3D8, EWB_C3D20, EWB_C3D8TL = 0, 1, 2
+EWB_C3D8, EWB_C3D20, EWB_C3D8TL, EWB_C3D8R, EWB_C3D8E, EWB_C3D20R = 0, 1, 2, 3, 4, 5
 EWB_MAT_LINEARELASTIC, EWB_MAT_VONMISES, EWB_MAT_NEOHOOKE_WA, EWB_MAT_NEOHOOKE_WB, EWB_MAT_NEOHOOKE_WC = 0, 1, 2, 3, 4
 EWB_OK, EWB_CUTBACK = 0, 1
 EWB_FLAG_ACCUMULATE_PF, EWB_FLAG_FORCE_GENERIC, EWB_FLAG_NO_STIFFNESS, EWB_FLAG_STAGED = 1, 2, 4, 8
 
-ELEMENT_CODES = {"C3D8": EWB_C3D8, "C3D8N": EWB_C3D8, "C3D20": EWB_C3D20, "C3D20N": EWB_C3D20, "C3D8TL": EWB_C3D8TL, "C3D8NTL": EWB_C3D8TL}
-ELEMENT_NODES = {EWB_C3D8: 8, EWB_C3D20: 20, EWB_C3D8TL: 8}
-ELEMENT_GAUSS = {EWB_C3D8: 8, EWB_C3D20: 27, EWB_C3D8TL: 8}
+ELEMENT_CODES = {"C3D8": EWB_C3D8, "C3D8N": EWB_C3D8, "C3D20": EWB_C3D20, "C3D20N": EWB_C3D20, "C3D8TL": EWB_C3D8TL, "C3D8NTL": EWB_C3D8TL,
+                 "C3D8R": EWB_C3D8R, "C3D8E": EWB_C3D8E, "C3D20R": EWB_C3D20R}
+ELEMENT_NODES = {EWB_C3D8: 8, EWB_C3D20: 20, EWB_C3D8TL: 8, EWB_C3D8R: 8, EWB_C3D8E: 8, EWB_C3D20R: 20}
+ELEMENT_GAUSS = {EWB_C3D8: 8, EWB_C3D20: 27, EWB_C3D8TL: 8, EWB_C3D8R: 1, EWB_C3D8E: 27, EWB_C3D20R: 8}
 MATERIAL_CODES = {
     "linearelastic": EWB_MAT_LINEARELASTIC,
     "vonmises": EWB_MAT_VONMISES,

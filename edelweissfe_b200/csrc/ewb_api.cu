@@ -76,6 +76,9 @@ int elementInfo(int elType, int* nn, int* ngp) {
         case EWB_C3D8: *nn = 8; *ngp = 8; return EWB_OK;
         case EWB_C3D8TL: *nn = 8; *ngp = 8; return EWB_OK;
         case EWB_C3D20: *nn = 20; *ngp = 27; return EWB_OK;
+        case EWB_C3D8R: *nn = 8; *ngp = 1; return EWB_OK;
+        case EWB_C3D8E: *nn = 8; *ngp = 27; return EWB_OK;
+        case EWB_C3D20R: *nn = 20; *ngp = 8; return EWB_OK;
     }
     return fail(EWB_ERR_UNSUPPORTED, "unknown element type");
 }
@@ -129,6 +132,15 @@ int dispatchVij(ewb_plan* p, int mc, const ewb::MatParams& mp, const ewb_buffers
     } else if (p->elType == EWB_C3D20) {
         if (mc == ewb::MC_LE) return launchVij<20, 27, ewb::MC_LE, false, 32, 4, 6>(p, mp, b, V, Pe, st);
         if (mc == ewb::MC_VM) return launchVij<20, 27, ewb::MC_VM, false, 32, 4, 6>(p, mp, b, V, Pe, st);
+    } else if (p->elType == EWB_C3D8R) {
+        if (mc == ewb::MC_LE) return launchVij<8, 1, ewb::MC_LE, false, 8, 16, 5>(p, mp, b, V, Pe, st);
+        if (mc == ewb::MC_VM) return launchVij<8, 1, ewb::MC_VM, false, 8, 16, 5>(p, mp, b, V, Pe, st);
+    } else if (p->elType == EWB_C3D8E) {
+        if (mc == ewb::MC_LE) return launchVij<8, 27, ewb::MC_LE, false, 32, 4, 5>(p, mp, b, V, Pe, st);
+        if (mc == ewb::MC_VM) return launchVij<8, 27, ewb::MC_VM, false, 32, 4, 5>(p, mp, b, V, Pe, st);
+    } else if (p->elType == EWB_C3D20R) {
+        if (mc == ewb::MC_LE) return launchVij<20, 8, ewb::MC_LE, false, 32, 4, 6>(p, mp, b, V, Pe, st);
+        if (mc == ewb::MC_VM) return launchVij<20, 8, ewb::MC_VM, false, 32, 4, 6>(p, mp, b, V, Pe, st);
     }
     return fail(EWB_ERR_UNSUPPORTED, "element/material combination not implemented");
 }
@@ -437,8 +449,14 @@ int ewb_body_force(ewb_plan* p, const double* coords_dev, const double load_host
     if (!p->peScratch) CUDA_TRY(cudaMalloc((void**)&p->peScratch, (size_t)p->nEl * nd * sizeof(double)));
     const int B = 128;
     const unsigned grid = (unsigned)((p->nEl + B - 1) / B);
-    if (p->nn == 8) ewb::bodyForceKernel<8, 8><<<grid, B, 0, st>>>(p->nEl, p->conn, coords_dev, load_host[0], load_host[1], load_host[2], p->peScratch);
-    else ewb::bodyForceKernel<20, 27><<<grid, B, 0, st>>>(p->nEl, p->conn, coords_dev, load_host[0], load_host[1], load_host[2], p->peScratch);
+#define EWB_BF(NN_, NGP_) ewb::bodyForceKernel<NN_, NGP_><<<grid, B, 0, st>>>(p->nEl, p->conn, coords_dev, load_host[0], load_host[1], load_host[2], p->peScratch)
+    if (p->nn == 8 && p->ngp == 8) EWB_BF(8, 8);
+    else if (p->nn == 8 && p->ngp == 1) EWB_BF(8, 1);
+    else if (p->nn == 8 && p->ngp == 27) EWB_BF(8, 27);
+    else if (p->nn == 20 && p->ngp == 27) EWB_BF(20, 27);
+    else if (p->nn == 20 && p->ngp == 8) EWB_BF(20, 8);
+    else return fail(EWB_ERR_UNSUPPORTED, "ewb_body_force: element type not implemented");
+#undef EWB_BF
     LAUNCH_CHECK();
     const unsigned g2 = (unsigned)((3 * p->nNode + 255) / 256);
     if (p->nn == 8) ewb::gatherLoadKernel<8><<<g2, 256, 0, st>>>(p->nNode, p->incPtr, p->inc, p->peScratch, pext_dev);

@@ -63,6 +63,12 @@ template <> struct Gauss<8> {
         w = 1.0;
     }
 };
+template <> struct Gauss<1> {  // C3D8R: elements/library.py:228-243
+    __device__ static void get(int, double& xi, double& eta, double& zeta, double& w) {
+        xi = eta = zeta = 0.0;
+        w = 8.0;
+    }
+};
 template <> struct Gauss<27> {
     __device__ static void get(int gp, double& xi, double& eta, double& zeta, double& w) {
         const double r = 0.77459666924148337704;  // sqrt(0.6)

@@ -39,7 +39,7 @@ _MATERIAL_BY_CLASS = {
     "NeoHookeanWbMaterial": ("neohookewb", lambda m: [m._mu, m._K]),
     "NeoHookeanWcMaterial": ("neohookewc", lambda m: [m._mu, m._K]),
 }
-_SUPPORTED_ELTYPES = {"C3D8", "C3D8N", "C3D20", "C3D20N", "C3D8TL", "C3D8NTL"}
+_SUPPORTED_ELTYPES = {"C3D8", "C3D8N", "C3D20", "C3D20N", "C3D8TL", "C3D8NTL", "C3D8R", "C3D8E", "C3D20R"}
 
 
 def default_backend(elType, conn, coords, material, props, box=None):
@@ -73,7 +73,8 @@ class ElementSetExtraction:
         self.material, getprops = _MATERIAL_BY_CLASS[type(mat).__name__]
         self.props = [float(p) for p in getprops(mat)]
         tl = type(els[0]).__name__ == "DisplacementTLElement"
-        self.elType = {(8, 8, False): "C3D8", (20, 27, False): "C3D20", (8, 8, True): "C3D8TL"}.get((nn, nInt, tl))
+        self.elType = {(8, 8, False): "C3D8", (20, 27, False): "C3D20", (8, 8, True): "C3D8TL", (8, 1, False): "C3D8R", (8, 27, False): "C3D8E",
+                       (20, 8, False): "C3D20R"}.get((nn, nInt, tl))
         if self.elType is None:
             raise NotImplementedError(f"element with {nn} nodes / {nInt} Gauss points (TL={tl}) is not implemented on the device")
         # element dof lists straight from the reference's DofManager (numerics/dofmanager.py:445-471)

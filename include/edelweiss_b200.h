@@ -30,7 +30,13 @@ extern "C" {
 #endif
 
 /* element formulations (provider "edelweiss"; elements/library.py:212-227, 260-275, 453-468) */
-enum { EWB_C3D8 = 0, EWB_C3D20 = 1, EWB_C3D8TL = 2 };
+enum {
+    EWB_C3D8 = 0, EWB_C3D20 = 1, EWB_C3D8TL = 2,
+    /* integration variants of the small-strain element (elements/library.py:228-259, 276-291): arbitrary-mesh path */
+    EWB_C3D8R = 3,  /* 8 nodes, 1 Gauss point (weight 8)  */
+    EWB_C3D8E = 4,  /* 8 nodes, 3x3x3 Gauss points        */
+    EWB_C3D20R = 5  /* 20 nodes, 2x2x2 Gauss points       */
+};
 
 /* materials (materials/linearelastic, materials/vonmises, materials/neohooke) */
 enum {

@@ -8,7 +8,7 @@ from . import port
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libewb_oracle.so")
-_EL = {"C3D8": 0, "C3D20": 1, "C3D8TL": 2}
+_EL = {"C3D8": 0, "C3D20": 1, "C3D8TL": 2, "C3D8R": 3, "C3D8E": 4, "C3D20R": 5}
 _MAT = {"linearelastic": 0, "vonmises": 1, "neohookewa": 2, "neohookewb": 3, "neohookewc": 4}
 _inst = None
 

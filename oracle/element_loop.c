@@ -29,7 +29,7 @@
 #include <omp.h>
 #endif
 
-enum { EL_C3D8 = 0, EL_C3D20 = 1, EL_C3D8TL = 2 };
+enum { EL_C3D8 = 0, EL_C3D20 = 1, EL_C3D8TL = 2, EL_C3D8R = 3, EL_C3D8E = 4, EL_C3D20R = 5 }; /* 3..5: integration variants, library.py:228-259, 276-291 */
 enum { MAT_LE = 0, MAT_VM = 1, MAT_NHA = 2, MAT_NHB = 3, MAT_NHC = 4 };
 
 static const int OFF8[8][3] = {{0, 0, 0}, {0, 0, 1}, {1, 0, 1}, {1, 0, 0}, {0, 1, 0}, {0, 1, 1}, {1, 1, 1}, {1, 1, 0}};
@@ -69,7 +69,9 @@ static void shape_derivs(int nn, double X, double E, double Z, double dN[3][20])
 }
 
 static void gauss(int ngp, int g, double* xi, double* eta, double* zeta, double* w) {
-    if (ngp == 8) { /* elements/library.py:38-39, 212-227 */
+    if (ngp == 1) { /* elements/library.py:228-243: reduced integration */
+        *xi = *eta = *zeta = 0.0; *w = 8.0;
+    } else if (ngp == 8) { /* elements/library.py:38-39, 212-227 */
         const double q = 1.0 / sqrt(3.0);
         static const double s8[4] = {-1, 1, 1, -1}, t8[4] = {-1, -1, 1, 1};
         *xi = (g < 4 ? -q : q); *eta = q * t8[g % 4]; *zeta = q * s8[g % 4]; *w = 1.0;
@@ -315,7 +317,8 @@ int ewo_threads(void) {
 /* NISTParallel.computeElements loop body (mk2.pyx:157-184): every element writes its own VIJ slice and Pe slab */
 int ewo_compute_elements(int eltype, int material, const double* props, int64_t nEl, const int32_t* conn, const double* coords, const double* U,
                          const double* dU, const double* stateRef, double* stateTemp, double* V, double* Pe, int nthreads) {
-    const int nn = (eltype == EL_C3D20) ? 20 : 8, ngp = (eltype == EL_C3D20) ? 27 : 8;
+    const int nn = (eltype == EL_C3D20 || eltype == EL_C3D20R) ? 20 : 8;
+    const int ngp = (eltype == EL_C3D20 || eltype == EL_C3D8E) ? 27 : (eltype == EL_C3D8R ? 1 : 8);
     const int nstate = 12 + (material == MAT_LE ? 0 : 1), nd = 3 * nn;
     int failedAny = 0;
 #ifdef _OPENMP

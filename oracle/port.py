@@ -52,6 +52,9 @@ def gauss_points(eltype: str):
         t8 = g * np.array([-1, -1, 1, 1.0])
         xi = g * np.hstack([-np.ones(4), np.ones(4)])
         return xi, np.hstack([t8, t8]), np.hstack([s8, s8]), np.ones(8)
+    if t == "C3D8R":  # reduced integration: one point, weight 8 (library.py:228-243)
+        z = np.zeros(1)
+        return z, z.copy(), z.copy(), np.array([8.0])
     if t in ("C3D20", "C3D8E", "C3D20TL"):
         r = np.sqrt(0.6)
         s20 = np.array([-1, 0, 1.0])
@@ -98,6 +101,10 @@ ELEMENT_INFO = {
     "C3D8": dict(nnodes=8, tl=False),
     "C3D20": dict(nnodes=20, tl=False),
     "C3D8TL": dict(nnodes=8, tl=True),
+    # integration variants (library.py:228-259, 276-291): same formulation, other Gauss rule
+    "C3D8R": dict(nnodes=8, tl=False),
+    "C3D8E": dict(nnodes=8, tl=False),
+    "C3D20R": dict(nnodes=20, tl=False),
 }
 
 # number of material state variables; ref: materials/linearelastic/linearelastic.py:49-57,

@@ -28,6 +28,11 @@ CASES = [
     ("c3d20_le_affine", "C3D20", "linearelastic", [2.1e4, 0.22], dict(nX=2, nY=2, nZ=1, lX=2.0, lY=2.4, lZ=1.1), "affine", [1e-3]),
     ("c3d8tl_nha_distorted", "C3D8TL", "neohookewa", [91304.34783, 100000.0], dict(nX=3, nY=4, nZ=2, lX=3.0, lY=4.5, lZ=2.2), 0.2, [3e-2, 2e-2]),
     ("c3d8tl_nhb_distorted", "C3D8TL", "neohookewb", [91304.34783, 100000.0], dict(nX=3, nY=4, nZ=2, lX=3.0, lY=4.5, lZ=2.2), 0.2, [3e-2, 2e-2]),
+    # integration variants of the same formulation (library.py:228-259, 276-291)
+    ("c3d8r_le_distorted", "C3D8R", "linearelastic", [2.1e4, 0.22], dict(nX=3, nY=3, nZ=2, lX=3.0, lY=3.3, lZ=2.2), 0.2, [1e-3, 1e-3]),
+    ("c3d8r_vm_distorted", "C3D8R", "vonmises", [2.1e4, 0.22, 355, 1000, 200, 1400], dict(nX=3, nY=3, nZ=2, lX=3.0, lY=3.3, lZ=2.2), 0.2, [1.5e-2, 1e-2]),
+    ("c3d8e_vm_distorted", "C3D8E", "vonmises", [2.1e4, 0.22, 355, 1000, 200, 1400], dict(nX=2, nY=3, nZ=2, lX=2.0, lY=3.3, lZ=2.2), 0.2, [6e-3, 4e-3]),
+    ("c3d20r_le_box", "C3D20R", "linearelastic", [2.1e4, 0.22], dict(nX=2, nY=2, nZ=2, lX=2.0, lY=2.2, lZ=2.4), 0.0, [1e-3, 1e-3]),
     ("c3d8tl_nhc_distorted", "C3D8TL", "neohookewc", [91304.34783, 100000.0], dict(nX=3, nY=4, nZ=2, lX=3.0, lY=4.5, lZ=2.2), 0.2, [3e-2, 2e-2]),
 ]
 
