@@ -53,7 +53,7 @@ class COracle:
         failed = self.lib.ewo_compute_elements(el, mat, _p(props), nEl, _p(conn), _p(coords), _p(U), _p(dU), _p(stateRef), _p(stateTemp), _p(V), _p(Pe), nthreads)
         return V, Pe, stateTemp, bool(failed)
 
-    def assemble(self, elType, material, props, coords, conn, U, dU, stateRef, x=None, nnz=None):
+    def assemble(self, elType, material, props, coords, conn, U, dU, stateRef, x=None, nnz=None, nthreads=0):
         """computeElements + serial P/F scatter + updateCSR (pattern from oracle.port)."""
         conn = np.ascontiguousarray(conn, dtype=np.int32)
         nDof = 3 * coords.shape[0]
@@ -64,7 +64,7 @@ class COracle:
             indptr, indices, x = port.csr_pattern(I, J, nDof)
             nnz = indices.size
             out.update(indptr=indptr, indices=indices, x=x)
-        V, Pe, stateTemp, failed = self.compute_elements(elType, material, props, coords, conn, U, dU, stateRef)
+        V, Pe, stateTemp, failed = self.compute_elements(elType, material, props, coords, conn, U, dU, stateRef, nthreads=nthreads)
         P, F = np.zeros(nDof), np.zeros(nDof)
         self.lib.ewo_scatter_pf(conn.shape[0], conn.shape[1], _p(conn), _p(Pe), _p(P), _p(F))
         data = np.empty(nnz)
@@ -73,7 +73,7 @@ class COracle:
         out.update(V=V, data=data, P=P, F=F, stateTemp=stateTemp, failed=failed)
         return out
 
-    def make_runner(self, elType, material, props, coords, conn, U, dU, stateRef):
+    def make_runner(self, elType, material, props, coords, conn, U, dU, stateRef, nthreads=0):
         conn = np.ascontiguousarray(conn, dtype=np.int32)
         dofs = port.element_dofs(conn)
         I, J = port.vij_pattern(dofs)  # noqa: E741
@@ -81,7 +81,7 @@ class COracle:
         nnz = indices.size
 
         def run():
-            return self.assemble(elType, material, props, coords, conn, U, dU, stateRef, x=x, nnz=nnz)
+            return self.assemble(elType, material, props, coords, conn, U, dU, stateRef, x=x, nnz=nnz, nthreads=nthreads)
 
         return run
 

@@ -35,8 +35,13 @@ def run(workload, sample_n, steps=1, warmup=0):
     except Exception:
         impl = None
     if impl is not None and impl.supports(elType, material):
-        runner = impl.make_runner(elType, material, props, coords, conn, dU, dU, state)
-        cores, kind_note = impl.threads(), "C/OpenMP restatement of the reference algorithm (oracle/element_loop.c)"
+        # every host thread this process may use, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        runner = impl.make_runner(elType, material, props, coords, conn, dU, dU, state, nthreads=cores)
+        kind_note = "C/OpenMP restatement of the reference algorithm (oracle/element_loop.c)"
     else:
         # pattern once (reference: per step), then the loop body per timed step
         dofs = port.element_dofs(conn)
