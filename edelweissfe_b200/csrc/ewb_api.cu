@@ -88,16 +88,15 @@ int materialClass(int elType, int material, const double* props, int nProps, ewb
     mp->kind = material;
     const bool tl = (elType == EWB_C3D8TL);
     if (material == EWB_MAT_LINEARELASTIC || material == EWB_MAT_VONMISES) {
-        if (tl) return fail(EWB_ERR_UNSUPPORTED, "C3D8TL with hypo-elastic materials (geometric-stiffness branch, element.py:415-425) is not implemented");
         if (nProps < (material == EWB_MAT_VONMISES ? 6 : 2)) return fail(EWB_ERR_ARG, "too few material properties");
         const double E = props[0], v = props[1];
         mp->lambda = E * v / ((1.0 + v) * (1.0 - 2.0 * v));
         mp->G = E / (2.0 * (1.0 + v));
         if (material == EWB_MAT_VONMISES) {
             mp->fy0 = props[2]; mp->HLin = props[3]; mp->dfy = props[4]; mp->delta = props[5];
-            *mc = ewb::MC_VM; *nMatState = 1;
+            *mc = tl ? ewb::MC_TLV : ewb::MC_VM; *nMatState = 1;
         } else {
-            *mc = ewb::MC_LE; *nMatState = 0;
+            *mc = tl ? ewb::MC_TLE : ewb::MC_LE; *nMatState = 0;
         }
         return EWB_OK;
     }
@@ -129,6 +128,8 @@ int dispatchVij(ewb_plan* p, int mc, const ewb::MatParams& mp, const ewb_buffers
         if (mc == ewb::MC_VM) return launchVij<8, 8, ewb::MC_VM, false, 8, 16, 5>(p, mp, b, V, Pe, st);
     } else if (p->elType == EWB_C3D8TL) {
         if (mc == ewb::MC_NH) return launchVij<8, 8, ewb::MC_NH, true, 8, 16, 5>(p, mp, b, V, Pe, st);
+        if (mc == ewb::MC_TLE) return launchVij<8, 8, ewb::MC_TLE, true, 8, 16, 5>(p, mp, b, V, Pe, st);  // element.py:415-425
+        if (mc == ewb::MC_TLV) return launchVij<8, 8, ewb::MC_TLV, true, 8, 16, 5>(p, mp, b, V, Pe, st);
     } else if (p->elType == EWB_C3D20) {
         if (mc == ewb::MC_LE) return launchVij<20, 27, ewb::MC_LE, false, 32, 4, 6>(p, mp, b, V, Pe, st);
         if (mc == ewb::MC_VM) return launchVij<20, 27, ewb::MC_VM, false, 32, 4, 6>(p, mp, b, V, Pe, st);

@@ -15,7 +15,11 @@
 
 namespace ewb {
 
-enum : int { MC_LE = 0, MC_VM = 1, MC_NH = 2 };  // material classes (kernel template parameter)
+// material classes (kernel template parameter).  MC_TLE / MC_TLV: linear elastic / von Mises inside the total-Lagrange
+// element (non-hyperelastic branch with geometric stiffness, displacementtlelement/element.py:415-425); arbitrary-mesh path only.
+enum : int { MC_LE = 0, MC_VM = 1, MC_NH = 2, MC_TLE = 3, MC_TLV = 4 };
+__host__ __device__ constexpr int matStateCount(int mc) { return (mc == MC_LE || mc == MC_TLE) ? 0 : 1; }
+__host__ __device__ constexpr bool isHypoTL(int mc) { return mc == MC_TLE || mc == MC_TLV; }
 
 // Material parameters, preprocessed on the host and passed by value.
 struct MatParams {

@@ -37,10 +37,13 @@ struct TileLayout {
     static constexpr int GST = NN * 3 + 1;  // Gauss-point stride of the vector tables (odd: conflict-light)
     // per-Gauss-point scalars: [0..3] tangent coefficients (already * w detJ), [4..9] -w detJ * stress
     // (tensor order xx,yy,zz,xy,xz,yz), [10..18] F (only W_b needs it in phase B)
-    static constexpr int NCO = 20;
+    // hypo-elastic TL: [10..18] F, [20..25] w detJ mu' (F F^T) (xx,yy,zz,xy,xz,yz); Q holds f_a = F grad N_a, R holds p_a = F N grad N_a
+    static constexpr bool HASR = (MC == MC_TLV);
+    static constexpr int NCO = isHypoTL(MC) ? 26 : 20;
     static constexpr int OFF_G = 0;
     static constexpr int OFF_Q = OFF_G + NGP * GST;
-    static constexpr int OFF_CO = OFF_Q + (HASQ ? NGP * GST : 0);
+    static constexpr int OFF_R = OFF_Q + (HASQ ? NGP * GST : 0);
+    static constexpr int OFF_CO = OFF_R + (HASR ? NGP * GST : 0);
     static constexpr int OFF_X = OFF_CO + NGP * NCO;  // nodal X, dU, U: [3][NN][3]
     static constexpr int RAW = OFF_X + 9 * NN;
     static constexpr int PER_EL = RAW + ((8 - RAW % 16) + 16) % 16;  // == 8 (mod 16) doubles: see DESIGN.md (banks)
@@ -113,7 +116,7 @@ __device__ __forceinline__ void gaussPointL(double* sm, const double* X, const d
 
     double st[13];
 #pragma unroll
-    for (int c = 0; c < 12 + (MC != MC_LE ? 1 : 0); ++c) st[c] = state_ref[c * cstride];
+    for (int c = 0; c < 12 + matStateCount(MC); ++c) st[c] = state_ref[c * cstride];
 
     if constexpr (!TL) {
         // Voigt 11,22,33,12,13,23 with engineering shear (_B3D8)
@@ -149,6 +152,83 @@ __device__ __forceinline__ void gaussPointL(double* sm, const double* X, const d
         // -w detJ * stress as a tensor (xx,yy,zz,xy,xz,yz): Voigt 3,4,5 = 12,13,23
 #pragma unroll
         for (int i = 0; i < 6; ++i) CO[4 + i] = -wd * s[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            st[i] = s[i];
+            st[6 + i] += de[i];
+        }
+    } else if constexpr (isHypoTL(MC)) {
+        // total Lagrange with a small-strain material law on (PK2, Green-Lagrange increment): element.py:415-425
+        double F[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) F[i] = H[i];
+        F[0] += 1.0;
+        F[4] += 1.0;
+        F[8] += 1.0;
+        // E = (H + H^T + H^T H)/2, Voigt 11,22,33,2*12,2*23,2*13 (voigtnotation.py:32-52); E_old = accepted strain state
+        double E[6];
+        E[0] = H[0] + 0.5 * (H[0] * H[0] + H[3] * H[3] + H[6] * H[6]);
+        E[1] = H[4] + 0.5 * (H[1] * H[1] + H[4] * H[4] + H[7] * H[7]);
+        E[2] = H[8] + 0.5 * (H[2] * H[2] + H[5] * H[5] + H[8] * H[8]);
+        E[3] = H[1] + H[3] + H[0] * H[1] + H[3] * H[4] + H[6] * H[7];
+        E[4] = H[5] + H[7] + H[1] * H[2] + H[4] * H[5] + H[7] * H[8];
+        E[5] = H[2] + H[6] + H[0] * H[2] + H[3] * H[5] + H[6] * H[8];
+        double de[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) de[i] = E[i] - st[6 + i];
+        double s[6] = {st[0], st[1], st[2], st[3], st[4], st[5]};  // PK2, Voigt 11,22,33,12,23,13
+        double cm;
+        double* Q = sm + L::OFF_Q + gp * L::GST;
+        if constexpr (MC == MC_TLE) {
+            hookeAdd(mp, de, s);
+            CO[0] = wd * mp.lambda;
+            cm = wd * mp.G;
+            CO[2] = 0.0;
+        } else {
+            VMResult r;
+            double kappa = st[12];
+            vonMises(mp, de, s, kappa, r);
+            st[12] = kappa;
+            if (r.failed) atomicOr(failFlag, 1);
+            CO[0] = wd * r.lam;
+            cm = wd * r.mu;
+            CO[2] = -wd * r.a;
+            // p_a = B_a^T n = F N grad N_a, N = tensor(n), n Voigt 11,22,33,12,23,13
+            double* R = sm + L::OFF_R + gp * L::GST;
+            for (int a = 0; a < NN; ++a) {
+                const double gx = G[a * 3], gy = G[a * 3 + 1], gz = G[a * 3 + 2];
+                const double tx = r.n[0] * gx + r.n[3] * gy + r.n[5] * gz;
+                const double ty = r.n[3] * gx + r.n[1] * gy + r.n[4] * gz;
+                const double tz = r.n[5] * gx + r.n[4] * gy + r.n[2] * gz;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) R[a * 3 + k] = F[k * 3] * tx + F[k * 3 + 1] * ty + F[k * 3 + 2] * tz;
+            }
+        }
+        CO[1] = cm;
+        CO[3] = 0.0;
+        // -w detJ * S as a tensor (xx,yy,zz,xy,xz,yz): Voigt 3,4,5 = 12,23,13
+        CO[4] = -wd * s[0];
+        CO[5] = -wd * s[1];
+        CO[6] = -wd * s[2];
+        CO[7] = -wd * s[3];
+        CO[8] = -wd * s[5];
+        CO[9] = -wd * s[4];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) CO[10 + i] = F[i];
+        CO[19] = 0.0;
+        // w detJ mu' (F F^T)
+        CO[20] = cm * (F[0] * F[0] + F[1] * F[1] + F[2] * F[2]);
+        CO[21] = cm * (F[3] * F[3] + F[4] * F[4] + F[5] * F[5]);
+        CO[22] = cm * (F[6] * F[6] + F[7] * F[7] + F[8] * F[8]);
+        CO[23] = cm * (F[0] * F[3] + F[1] * F[4] + F[2] * F[5]);
+        CO[24] = cm * (F[0] * F[6] + F[1] * F[7] + F[2] * F[8]);
+        CO[25] = cm * (F[3] * F[6] + F[4] * F[7] + F[5] * F[8]);
+        // f_a = F grad N_a
+        for (int a = 0; a < NN; ++a) {
+            const double gx = G[a * 3], gy = G[a * 3 + 1], gz = G[a * 3 + 2];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) Q[a * 3 + k] = F[k * 3] * gx + F[k * 3 + 1] * gy + F[k * 3 + 2] * gz;
+        }
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             st[i] = s[i];
@@ -211,7 +291,7 @@ __device__ __forceinline__ void gaussPointL(double* sm, const double* X, const d
     }
     if (writeState) {
 #pragma unroll
-        for (int c = 0; c < 12 + (MC != MC_LE ? 1 : 0); ++c) state_temp[c * cstride] = st[c];
+        for (int c = 0; c < 12 + matStateCount(MC); ++c) state_temp[c * cstride] = st[c];
     }
 }
 
@@ -246,9 +326,18 @@ __device__ __forceinline__ void nodeRow(const double* sm, int a, const MatParams
             const double* v = (MC == MC_NH ? Q : G) + gp * L::GST + a * 3;
             const double* S = CO + gp * L::NCO + 4;
             const double vx = v[0], vy = v[1], vz = v[2];
-            P[0] += S[0] * vx + S[3] * vy + S[4] * vz;
-            P[1] += S[3] * vx + S[1] * vy + S[5] * vz;
-            P[2] += S[4] * vx + S[5] * vy + S[2] * vz;
+            const double t0 = S[0] * vx + S[3] * vy + S[4] * vz;
+            const double t1 = S[3] * vx + S[1] * vy + S[5] * vz;
+            const double t2 = S[4] * vx + S[5] * vy + S[2] * vz;
+            if constexpr (isHypoTL(MC)) {  // P_a = -w detJ B_a^T S = F ((-w detJ S) grad N_a)
+                const double* F = CO + gp * L::NCO + 10;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) P[k] += F[k * 3] * t0 + F[k * 3 + 1] * t1 + F[k * 3 + 2] * t2;
+            } else {
+                P[0] += t0;
+                P[1] += t1;
+                P[2] += t2;
+            }
         }
         emit.residual(a, P);
     }
@@ -312,6 +401,59 @@ __device__ __forceinline__ void nodeRow(const double* sm, int a, const MatParams
                         acc[k][0] += dot;
                         acc[k][4] += dot;
                         acc[k][8] += dot;
+                    }
+                }
+            } else if constexpr (isHypoTL(MC)) {
+                // K_ab = lam' f_a f_b^T + mu' f_b f_a^T + (g_a.g_b) mu' F F^T + (g_a^T S g_b) I - a p_a p_b^T   (all * w detJ)
+                const double cl = co[0], cm = co[1], ca = co[2];
+                const double* Rg = sm + L::OFF_R + gp * L::GST;
+                const double fa[3] = {Qg[a * 3], Qg[a * 3 + 1], Qg[a * 3 + 2]};
+                const double la[3] = {cl * fa[0], cl * fa[1], cl * fa[2]};
+                const double ma[3] = {cm * fa[0], cm * fa[1], cm * fa[2]};
+                double ra[3] = {0, 0, 0};
+                if constexpr (L::HASR) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) ra[i] = ca * Rg[a * 3 + i];
+                }
+                // (w detJ S) g_a  (co[4..9] holds -w detJ S)
+                const double sa[3] = {-(co[4] * ga[0] + co[7] * ga[1] + co[8] * ga[2]), -(co[7] * ga[0] + co[5] * ga[1] + co[9] * ga[2]),
+                                      -(co[8] * ga[0] + co[9] * ga[1] + co[6] * ga[2])};
+                const double* Bm = co + 20;
+#pragma unroll
+                for (int k = 0; k < BLK; ++k) {
+                    const int d = pass * BLK + k;
+                    if (d < nb) {
+                        int b = a + d;
+                        if (b >= NN) b -= NN;
+                        const double gb[3] = {Gg[b * 3], Gg[b * 3 + 1], Gg[b * 3 + 2]};
+                        const double fb[3] = {Qg[b * 3], Qg[b * 3 + 1], Qg[b * 3 + 2]};
+                        const double gg = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
+                        const double geo = sa[0] * gb[0] + sa[1] * gb[1] + sa[2] * gb[2];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) {
+                                double v = acc[k][i * 3 + j];
+                                v = fma(la[i], fb[j], v);
+                                v = fma(fb[i], ma[j], v);
+                                acc[k][i * 3 + j] = v;
+                            }
+                        if constexpr (L::HASR) {
+                            const double pb[3] = {Rg[b * 3], Rg[b * 3 + 1], Rg[b * 3 + 2]};
+#pragma unroll
+                            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                                for (int j = 0; j < 3; ++j) acc[k][i * 3 + j] = fma(ra[i], pb[j], acc[k][i * 3 + j]);
+                        }
+                        acc[k][0] += gg * Bm[0] + geo;
+                        acc[k][4] += gg * Bm[1] + geo;
+                        acc[k][8] += gg * Bm[2] + geo;
+                        acc[k][1] += gg * Bm[3];
+                        acc[k][3] += gg * Bm[3];
+                        acc[k][2] += gg * Bm[4];
+                        acc[k][6] += gg * Bm[4];
+                        acc[k][5] += gg * Bm[5];
+                        acc[k][7] += gg * Bm[5];
                     }
                 }
             } else {

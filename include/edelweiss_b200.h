@@ -31,7 +31,9 @@ extern "C" {
 
 /* element formulations (provider "edelweiss"; elements/library.py:212-227, 260-275, 453-468) */
 enum {
-    EWB_C3D8 = 0, EWB_C3D20 = 1, EWB_C3D8TL = 2,
+    EWB_C3D8 = 0, EWB_C3D20 = 1,
+    EWB_C3D8TL = 2, /* total Lagrange: Neo-Hooke (hyperelastic branch, element.py:391-414) on every path; linear elastic /
+                       von Mises (B^T C B + geometric stiffness, element.py:415-425) on the arbitrary-mesh path */
     /* integration variants of the small-strain element (elements/library.py:228-259, 276-291): arbitrary-mesh path */
     EWB_C3D8R = 3,  /* 8 nodes, 1 Gauss point (weight 8)  */
     EWB_C3D8E = 4,  /* 8 nodes, 3x3x3 Gauss points        */

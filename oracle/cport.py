@@ -37,7 +37,7 @@ class COracle:
     @staticmethod
     def supports(elType, material):
         tl = elType.upper() == "C3D8TL"
-        return elType.upper() in _EL and material.lower() in _MAT and (tl == material.lower().startswith("neohooke"))
+        return elType.upper() in _EL and material.lower() in _MAT and (tl or not material.lower().startswith("neohooke"))
 
     def compute_elements(self, elType, material, props, coords, conn, U, dU, stateRef, nthreads=0):
         el, mat = _EL[elType.upper()], _MAT[material.lower()]

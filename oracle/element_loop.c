@@ -257,6 +257,65 @@ static int compute_element(int eltype, int material, const double* props, int nn
                 Pe[p] -= acc * scale;
             }
             for (int v = 0; v < 6; ++v) st[6 + v] += de[v];
+        } else if (material == MAT_LE || material == MAT_VM) {
+            /* total Lagrange, non-hyperelastic branch: B^T C B + Hgeo (displacementtlelement/element.py:415-425, :48-73);
+             * E_old is the strain part of the accepted state (Voigt, doubled shear), see oracle/port.py */
+            double F[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            for (int a = 0; a < nn; ++a)
+                for (int i = 0; i < 3; ++i)
+                    for (int c = 0; c < 3; ++c) F[i * 3 + c] += U[3 * a + i] * gN[c][a];
+            double H[9], Eg[9];
+            for (int i = 0; i < 9; ++i) H[i] = F[i] - (i % 4 == 0 ? 1.0 : 0.0);
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    double hh = 0;
+                    for (int k = 0; k < 3; ++k) hh += H[k * 3 + i] * H[k * 3 + j];
+                    Eg[i * 3 + j] = 0.5 * (H[i * 3 + j] + H[j * 3 + i] + hh);
+                }
+            const double Ev[6] = {Eg[0], Eg[4], Eg[8], 2 * Eg[1], 2 * Eg[5], 2 * Eg[2]}; /* 11,22,33,12,23,13 */
+            double de[6], C[36];
+            for (int v = 0; v < 6; ++v) de[v] = Ev[v] - st[6 + v];
+            if (material == MAT_LE) {
+                elasticity_matrix(props[0], props[1], C);
+                for (int i = 0; i < 6; ++i)
+                    for (int j = 0; j < 6; ++j) st[i] += C[i * 6 + j] * de[j];
+            } else {
+                failed |= von_mises(props, st, C, de, st + 12);
+            }
+            for (int a = 0; a < nn; ++a) /* _B03D, _elementcomputationmatrices.py:867-916 */
+                for (int k = 0; k < 3; ++k) {
+                    const double fx = F[k * 3], fy = F[k * 3 + 1], fz = F[k * 3 + 2];
+                    B[0][3 * a + k] = gN[0][a] * fx;
+                    B[1][3 * a + k] = gN[1][a] * fy;
+                    B[2][3 * a + k] = gN[2][a] * fz;
+                    B[3][3 * a + k] = gN[0][a] * fy + gN[1][a] * fx;
+                    B[4][3 * a + k] = gN[1][a] * fz + gN[2][a] * fy;
+                    B[5][3 * a + k] = gN[0][a] * fz + gN[2][a] * fx;
+                }
+            for (int v = 0; v < 6; ++v)
+                for (int q = 0; q < nd; ++q) {
+                    double acc = 0;
+                    for (int u = 0; u < 6; ++u) acc += C[v * 6 + u] * B[u][q];
+                    CB[v][q] = acc;
+                }
+            const double S[9] = {st[0], st[3], st[5], st[3], st[1], st[4], st[5], st[4], st[2]};
+            for (int p = 0; p < nd; ++p)
+                for (int q = 0; q < nd; ++q) {
+                    double acc = 0;
+                    for (int v = 0; v < 6; ++v) acc += B[v][p] * CB[v][q];
+                    if (p % 3 == q % 3) { /* Hgeo: (grad N_a . S . grad N_b) I */
+                        const int a = p / 3, b = q / 3;
+                        for (int i = 0; i < 3; ++i)
+                            for (int j = 0; j < 3; ++j) acc += gN[i][a] * S[i * 3 + j] * gN[j][b];
+                    }
+                    Ke[p * nd + q] += acc * scale;
+                }
+            for (int p = 0; p < nd; ++p) {
+                double acc = 0;
+                for (int v = 0; v < 6; ++v) acc += B[v][p] * st[v];
+                Pe[p] -= acc * scale;
+            }
+            for (int v = 0; v < 6; ++v) st[6 + v] += de[v];
         } else {
             double F[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, iF[9], tau[9], A[81], energy;
             for (int a = 0; a < nn; ++a)

@@ -421,6 +421,71 @@ def compute_tl_hyperelastic(eltype, material, props, X, Ue, dUe, stateRef):
     return Ke, Pe, state, np.zeros(state.shape[:2], dtype=bool)
 
 
+def _unvoigt_stress(s):
+    """ref: utils/voigtnotation.py:95-113 (order 11,22,33,12,23,13)."""
+    T = np.empty(s.shape[:-1] + (3, 3))
+    T[..., 0, 0], T[..., 1, 1], T[..., 2, 2] = s[..., 0], s[..., 1], s[..., 2]
+    T[..., 0, 1] = T[..., 1, 0] = s[..., 3]
+    T[..., 1, 2] = T[..., 2, 1] = s[..., 4]
+    T[..., 0, 2] = T[..., 2, 0] = s[..., 5]
+    return T
+
+
+def b_operator_tl(F, gN):
+    """Nonlinear B [e,g,6,3n], Voigt rows 11,22,33,12,23,13 with engineering shear.
+    ref: elements/displacementtlelement/_elementcomputationmatrices.py:867-916 (_B03D)."""
+    e, g, _, nn = gN.shape
+    B = np.zeros((e, g, 6, nn, 3))
+    dX, dY, dZ = gN[:, :, 0, :, None], gN[:, :, 1, :, None], gN[:, :, 2, :, None]  # [e,g,a,1]
+    Fc = lambda c: F[:, :, None, :, c]  # noqa: E731  column c of F as [e,g,1,k]
+    B[:, :, 0] = dX * Fc(0)
+    B[:, :, 1] = dY * Fc(1)
+    B[:, :, 2] = dZ * Fc(2)
+    B[:, :, 3] = dX * Fc(1) + dY * Fc(0)
+    B[:, :, 4] = dY * Fc(2) + dZ * Fc(1)
+    B[:, :, 5] = dX * Fc(2) + dZ * Fc(0)
+    return B.reshape(e, g, 6, 3 * nn)
+
+
+def compute_tl_hypoelastic(eltype, material, props, X, Ue, dUe, stateRef):
+    """DisplacementTLElement.computeYourself, non-hyperelastic branch (material tangent B^T C B plus the geometric
+    stiffness Hgeo), batched.  ref: elements/displacementtlelement/element.py:373-427 (branch :415-425), Hgeo :48-73.
+    The element keeps the last accepted Green-Lagrange strain in `_Eold` (:215, :461); it equals the strain part of the
+    accepted state, [6:12] = sum of dStrain = Voigt(E_old), which is what this restatement (and the device) uses."""
+    nn = ELEMENT_INFO[eltype]["nnodes"]
+    xi, eta, zeta, w = gauss_points(eltype)
+    dN = shape_derivatives(nn, xi, eta, zeta)
+    J = jacobians(dN, X)
+    detJ = np.linalg.det(J)
+    gN = nabla_n(dN, J)  # [e,g,3,a]
+    u = Ue.reshape(Ue.shape[0], nn, 3)
+    F = np.eye(3)[None, None] + np.einsum("eai,egja->egij", u, gN)
+    H = F - np.eye(3)
+    Egl = 0.5 * (H + np.swapaxes(H, -1, -2) + np.swapaxes(H, -1, -2) @ H)
+    state = stateRef.copy()
+    dstrain = _voigt_strain(Egl) - state[..., 6:12]
+    stress0 = state[..., 0:6]
+    if material == "linearelastic":
+        stress, C, mstate, failed = linear_elastic(props, stress0, dstrain)
+    elif material == "vonmises":
+        stress, C, mstate, failed = von_mises(props, stress0, dstrain, state[..., 12])
+    else:
+        raise ValueError(material)
+    B = b_operator_tl(F, gN)
+    S = _unvoigt_stress(stress)
+    Hsub = np.einsum("egia,egij,egjb->egab", gN, S, gN)  # nablaN^T S nablaN
+    scale = detJ * w[None, :]
+    nd = 3 * nn
+    Ke = np.einsum("egvi,egvw,egwj,eg->eij", B, C, B, scale, optimize=True)
+    Ke = Ke + np.einsum("egab,kl,eg->eakbl", Hsub, np.eye(3), scale).reshape(-1, nd, nd)
+    Pe = -np.einsum("egvi,egv,eg->ei", B, stress, scale, optimize=True)
+    state[..., 0:6] = stress
+    state[..., 6:12] += dstrain
+    if mstate.shape[-1]:
+        state[..., 12:] = mstate
+    return Ke, Pe, state, failed
+
+
 def shape_functions_bodyforce(nnodes: int, xi, eta, zeta):
     """N[gp, a] as `computeNOperator` evaluates it (ref: displacementelement/_elementcomputationmatrices.py:106-212).
     Its node table has xi and eta swapped relative to the derivative tables: node a sits at
@@ -454,7 +519,10 @@ def compute_elements(eltype, material, props, coords, conn, U, dU, stateRef, chu
     eltype = eltype.upper()
     material = material.lower()
     dofs = element_dofs(conn)
-    fn = compute_tl_hyperelastic if ELEMENT_INFO[eltype]["tl"] else compute_small_strain
+    if ELEMENT_INFO[eltype]["tl"]:
+        fn = compute_tl_hyperelastic if material.startswith("neohooke") else compute_tl_hypoelastic  # element.py:333-334
+    else:
+        fn = compute_small_strain
     outs = []
     for s in range(0, conn.shape[0], chunk):
         sl = slice(s, s + chunk)

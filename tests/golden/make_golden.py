@@ -33,6 +33,9 @@ CASES = [
     ("c3d8r_vm_distorted", "C3D8R", "vonmises", [2.1e4, 0.22, 355, 1000, 200, 1400], dict(nX=3, nY=3, nZ=2, lX=3.0, lY=3.3, lZ=2.2), 0.2, [1.5e-2, 1e-2]),
     ("c3d8e_vm_distorted", "C3D8E", "vonmises", [2.1e4, 0.22, 355, 1000, 200, 1400], dict(nX=2, nY=3, nZ=2, lX=2.0, lY=3.3, lZ=2.2), 0.2, [6e-3, 4e-3]),
     ("c3d20r_le_box", "C3D20R", "linearelastic", [2.1e4, 0.22], dict(nX=2, nY=2, nZ=2, lX=2.0, lY=2.2, lZ=2.4), 0.0, [1e-3, 1e-3]),
+    # total-Lagrange element with hypo-elastic materials: B^T C B + geometric stiffness (displacementtlelement/element.py:415-425)
+    ("c3d8tl_le_distorted", "C3D8TL", "linearelastic", [2.1e4, 0.22], dict(nX=2, nY=3, nZ=2, lX=2.0, lY=3.3, lZ=2.2), 0.15, [2e-2, 1e-2, 1e-2]),
+    ("c3d8tl_vm_distorted", "C3D8TL", "vonmises", [2.1e4, 0.22, 355, 1000, 200, 1400], dict(nX=2, nY=3, nZ=2, lX=2.0, lY=3.3, lZ=2.2), 0.15, [1.2e-2, 8e-3, 5e-3]),
     ("c3d8tl_nhc_distorted", "C3D8TL", "neohookewc", [91304.34783, 100000.0], dict(nX=3, nY=4, nZ=2, lX=3.0, lY=4.5, lZ=2.2), 0.2, [3e-2, 2e-2]),
 ]
 
