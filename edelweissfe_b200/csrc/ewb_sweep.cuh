@@ -231,7 +231,7 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
 // raw tensor-pipe accumulators of one element in one lane (two node blocks: t = 0, 1)
 template <int MC> struct TileAcc;
 template <> struct TileAcc<MC_LE> { double c[3][3][2]; };
-template <> struct TileAcc<MC_VM> { double c1[3][3][2], c2[3][3][2]; };
+template <> struct TileAcc<MC_VM> { double c1[3][3][2], c2[3][3][2]; bool elastic; };  // elastic: all 8 Gauss points of the element stayed elastic
 template <> struct TileAcc<MC_NH> { double c1[3][3][2], c2[3][3][2], d0[3][2]; };
 
 template <int MC>
@@ -279,6 +279,10 @@ __device__ __forceinline__ void elementTiles(const double* T, int lane, const do
         for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j < 3; ++j) c1[i][j][0] = c1[i][j][1] = c2[i][j][0] = c2[i][j][1] = 0.0;
+        // An element whose 8 Gauss points all stayed elastic has the constant tangent (lam, mu, a = 0): one product
+        // M' = sum (w detJ mu grad N_a) grad N_b^T and K_ab = (lam/mu) M' + M'^T + tr(M') I (18 instead of 54 DMMA).
+        // The 32 lanes of the warp read all 8 records (q = 0..3, two k-steps), so the vote sees every Gauss point.
+        acc.elastic = __all_sync(0xffffffffu, rec0[R::C_CO + 2] == 0.0 && rec1[R::C_CO + 2] == 0.0);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
             const double* rec = ks ? rec1 : rec0;
@@ -288,7 +292,14 @@ __device__ __forceinline__ void elementTiles(const double* T, int lane, const do
             Pr[0] += S[0] * g[ks][0] + S[3] * g[ks][1] + S[4] * g[ks][2];
             Pr[1] += S[3] * g[ks][0] + S[1] * g[ks][1] + S[5] * g[ks][2];
             Pr[2] += S[4] * g[ks][0] + S[5] * g[ks][1] + S[2] * g[ks][2];
-            if (wantK) {
+            if (wantK && acc.elastic) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double mi = cm * g[ks][i];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) dmma(c2[i][j], mi, g[ks][j]);
+                }
+            } else if (wantK) {
                 // p_a = B_a^T n = N g_a, N = tensor(n)  (n Voigt 11,22,33,12,13,23)
                 double pv[3];
                 pv[0] = n[0] * g[ks][0] + n[3] * g[ks][1] + n[4] * g[ks][2];
@@ -383,10 +394,18 @@ __device__ __forceinline__ void finishBlock(const TileAcc<MC>& acc, int t, const
         }
     } else if constexpr (MC == MC_VM) {
         const double tr = acc.c2[0][0][t] + acc.c2[1][1][t] + acc.c2[2][2][t];
+        if (acc.elastic) {
+            const double lom = mp.lambda / mp.G;
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = acc.c1[i][j][t] + acc.c2[j][i][t] + (i == j ? tr : 0.0);
+                for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = fma(lom, acc.c2[i][j][t], acc.c2[j][i][t]) + (i == j ? tr : 0.0);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = acc.c1[i][j][t] + acc.c2[j][i][t] + (i == j ? tr : 0.0);
+        }
     } else {
         const double tr = acc.d0[0][t] + acc.d0[1][t] + acc.d0[2][t];
 #pragma unroll
