@@ -57,6 +57,7 @@ struct ewb_plan {
     int32_t* adj = nullptr;      // [nSlots]
     int64_t* incPtr = nullptr;   // [nNode+1]  node -> incident (element*nn + localNode), ascending element
     int32_t* inc = nullptr;
+    int maxDeg = 0;              // largest node degree (row-gather shared-memory size)
     int* failFlag = nullptr;     // device status word
     int* failHost = nullptr;     // pinned mirror
     double* peScratch = nullptr; // [nEl][3nn] per-element residual (generic path)
@@ -111,37 +112,37 @@ int materialClass(int elType, int material, const double* props, int nProps, ewb
 }
 
 template <int NN, int NGP, int MC, bool TL, int T, int E, int BLK>
-int launchVij(ewb_plan* p, const ewb::MatParams& mp, const ewb_buffers* b, double* V, double* Pe, cudaStream_t st) {
+int launchVij(ewb_plan* p, const ewb::MatParams& mp, const ewb_buffers* b, double* V, double* Pe, cudaStream_t st, int transposed) {
     using L = ewb::TileLayout<NN, NGP, MC>;
     auto kern = ewb::computeElementsVijKernel<NN, NGP, MC, TL, T, E, BLK>;
     const size_t smem = (size_t)E * L::PER_EL * sizeof(double);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = (p->nEl + E - 1) / E;
-    kern<<<(unsigned)grid, T * E, smem, st>>>(p->nEl, p->conn, b->coords, b->U, b->dU, b->state_ref, b->state_temp, V, Pe, mp, p->failFlag);
+    kern<<<(unsigned)grid, T * E, smem, st>>>(p->nEl, p->conn, b->coords, b->U, b->dU, b->state_ref, b->state_temp, V, Pe, mp, p->failFlag, transposed);
     LAUNCH_CHECK();
     return EWB_OK;
 }
 
-int dispatchVij(ewb_plan* p, int mc, const ewb::MatParams& mp, const ewb_buffers* b, double* V, double* Pe, cudaStream_t st) {
+int dispatchVij(ewb_plan* p, int mc, const ewb::MatParams& mp, const ewb_buffers* b, double* V, double* Pe, cudaStream_t st, int transposed = 0) {
     if (p->elType == EWB_C3D8) {
-        if (mc == ewb::MC_LE) return launchVij<8, 8, ewb::MC_LE, false, 8, 16, 5>(p, mp, b, V, Pe, st);
-        if (mc == ewb::MC_VM) return launchVij<8, 8, ewb::MC_VM, false, 8, 16, 5>(p, mp, b, V, Pe, st);
+        if (mc == ewb::MC_LE) return launchVij<8, 8, ewb::MC_LE, false, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_VM) return launchVij<8, 8, ewb::MC_VM, false, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
     } else if (p->elType == EWB_C3D8TL) {
-        if (mc == ewb::MC_NH) return launchVij<8, 8, ewb::MC_NH, true, 8, 16, 5>(p, mp, b, V, Pe, st);
-        if (mc == ewb::MC_TLE) return launchVij<8, 8, ewb::MC_TLE, true, 8, 16, 5>(p, mp, b, V, Pe, st);  // element.py:415-425
-        if (mc == ewb::MC_TLV) return launchVij<8, 8, ewb::MC_TLV, true, 8, 16, 5>(p, mp, b, V, Pe, st);
+        if (mc == ewb::MC_NH) return launchVij<8, 8, ewb::MC_NH, true, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_TLE) return launchVij<8, 8, ewb::MC_TLE, true, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);  // element.py:415-425
+        if (mc == ewb::MC_TLV) return launchVij<8, 8, ewb::MC_TLV, true, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
     } else if (p->elType == EWB_C3D20) {
-        if (mc == ewb::MC_LE) return launchVij<20, 27, ewb::MC_LE, false, 32, 4, 6>(p, mp, b, V, Pe, st);
-        if (mc == ewb::MC_VM) return launchVij<20, 27, ewb::MC_VM, false, 32, 4, 6>(p, mp, b, V, Pe, st);
+        if (mc == ewb::MC_LE) return launchVij<20, 27, ewb::MC_LE, false, 32, 4, 6>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_VM) return launchVij<20, 27, ewb::MC_VM, false, 32, 4, 6>(p, mp, b, V, Pe, st, transposed);
     } else if (p->elType == EWB_C3D8R) {
-        if (mc == ewb::MC_LE) return launchVij<8, 1, ewb::MC_LE, false, 8, 16, 5>(p, mp, b, V, Pe, st);
-        if (mc == ewb::MC_VM) return launchVij<8, 1, ewb::MC_VM, false, 8, 16, 5>(p, mp, b, V, Pe, st);
+        if (mc == ewb::MC_LE) return launchVij<8, 1, ewb::MC_LE, false, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_VM) return launchVij<8, 1, ewb::MC_VM, false, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
     } else if (p->elType == EWB_C3D8E) {
-        if (mc == ewb::MC_LE) return launchVij<8, 27, ewb::MC_LE, false, 32, 4, 5>(p, mp, b, V, Pe, st);
-        if (mc == ewb::MC_VM) return launchVij<8, 27, ewb::MC_VM, false, 32, 4, 5>(p, mp, b, V, Pe, st);
+        if (mc == ewb::MC_LE) return launchVij<8, 27, ewb::MC_LE, false, 32, 4, 5>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_VM) return launchVij<8, 27, ewb::MC_VM, false, 32, 4, 5>(p, mp, b, V, Pe, st, transposed);
     } else if (p->elType == EWB_C3D20R) {
-        if (mc == ewb::MC_LE) return launchVij<20, 8, ewb::MC_LE, false, 32, 4, 6>(p, mp, b, V, Pe, st);
-        if (mc == ewb::MC_VM) return launchVij<20, 8, ewb::MC_VM, false, 32, 4, 6>(p, mp, b, V, Pe, st);
+        if (mc == ewb::MC_LE) return launchVij<20, 8, ewb::MC_LE, false, 32, 4, 6>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_VM) return launchVij<20, 8, ewb::MC_VM, false, 32, 4, 6>(p, mp, b, V, Pe, st, transposed);
     }
     return fail(EWB_ERR_UNSUPPORTED, "element/material combination not implemented");
 }
@@ -203,6 +204,7 @@ int ewb_plan_create(ewb_plan** out, int el_type, int64_t n_el, int64_t n_node, c
     adj.reserve(adjPtr[n_node]);
     for (auto& c : chunks) { adj.insert(adj.end(), c.begin(), c.end()); std::vector<int32_t>().swap(c); }
     p->nSlots = adjPtr[n_node];
+    for (int64_t n = 0; n < n_node; ++n) p->maxDeg = std::max<int>(p->maxDeg, (int)(adjPtr[n + 1] - adjPtr[n]));
     p->nnz = 9 * p->nSlots;
     if (p->nnz >= (int64_t)1 << 31) { delete p; return fail(EWB_ERR_UNSUPPORTED, "nnz exceeds int32 CSR indices (csrgenerator.pyx uses C int)"); }
 
@@ -429,7 +431,8 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
             V = p->vijScratch;
         }
     }
-    if (int rc = dispatchVij(p, mc, mp, b, V, p->peScratch, st)) return rc;
+    const bool internalV = wantK && V == p->vijScratch;  // nobody else reads it: use the gather-friendly transposed layout
+    if (int rc = dispatchVij(p, mc, mp, b, V, p->peScratch, st, internalV ? 1 : 0)) return rc;
     {
         const int B = 256;
         const unsigned grid = (unsigned)((3 * p->nNode + B - 1) / B);
@@ -437,6 +440,20 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
         if (p->nn == 8) ewb::gatherResidualKernel<8><<<grid, B, 0, st>>>(p->nNode, p->incPtr, p->inc, p->peScratch, b->P, b->F, acc);
         else ewb::gatherResidualKernel<20><<<grid, B, 0, st>>>(p->nNode, p->incPtr, p->inc, p->peScratch, b->P, b->F, acc);
         LAUNCH_CHECK();
+    }
+    if (wantK && internalV) {
+        constexpr int W = 8;
+        const size_t smem = (size_t)W * 9 * p->maxDeg * sizeof(double);
+        const unsigned grid = (unsigned)((p->nNode + W - 1) / W);
+        if (p->nn == 8) {
+            CUDA_TRY(cudaFuncSetAttribute(ewb::rowGatherKernel<8, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ewb::rowGatherKernel<8, W><<<grid, W * 32, smem, st>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, V, b->csr_data, p->maxDeg);
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(ewb::rowGatherKernel<20, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ewb::rowGatherKernel<20, W><<<grid, W * 32, smem, st>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, V, b->csr_data, p->maxDeg);
+        }
+        LAUNCH_CHECK();
+        return EWB_OK;
     }
     if (wantK) return ewb_update_csr(p, V, b->csr_data, stream);
     return EWB_OK;

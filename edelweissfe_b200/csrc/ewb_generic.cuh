@@ -14,16 +14,20 @@ struct VijEmit {
     static constexpr int ND = 3 * NN;
     double* V;   // element slice [ND*ND] or nullptr
     double* Pe;  // element slice [ND]
+    // false: the reference's VIJ layout, Ke row-major (element.py:318).  true: internal scratch, Ke^T row-major, so that the rows
+    // of one node (global K gets Ke^T, dofmanager.py:552-553) are 3 contiguous runs of ND doubles for rowGatherKernel.
+    bool transposed;
     __device__ __forceinline__ void residual(int a, const double P[3]) const {
 #pragma unroll
         for (int i = 0; i < 3; ++i) Pe[3 * a + i] = P[i];
     }
     __device__ __forceinline__ void block(int a, int b, const double K[9]) const {
         if (V == nullptr) return;
+        double* d = transposed ? V + (3 * b) * ND + 3 * a : V + (3 * a) * ND + 3 * b;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) V[(3 * a + i) * ND + 3 * b + j] = K[i * 3 + j];
+            for (int j = 0; j < 3; ++j) d[transposed ? j * ND + i : i * ND + j] = K[i * 3 + j];
     }
 };
 
@@ -32,7 +36,8 @@ template <int NN, int NGP, int MC, bool TL, int T, int E, int BLK>
 __global__ void __launch_bounds__(T* E) computeElementsVijKernel(int64_t nEl, const int32_t* __restrict__ conn, const double* __restrict__ coords,
                                                                 const double* __restrict__ U, const double* __restrict__ dU,
                                                                 const double* __restrict__ stateRef, double* __restrict__ stateTemp,
-                                                                double* __restrict__ V, double* __restrict__ Pe, MatParams mp, int* failFlag) {
+                                                                double* __restrict__ V, double* __restrict__ Pe, MatParams mp, int* failFlag,
+                                                                int transposed) {
     using L = TileLayout<NN, NGP, MC>;
     extern __shared__ double smem[];
     const int el = threadIdx.x / T, t = threadIdx.x % T;
@@ -48,7 +53,7 @@ __global__ void __launch_bounds__(T* E) computeElementsVijKernel(int64_t nEl, co
     }
     __syncthreads();
     if (active && t < NN) {
-        VijEmit<NN> emit{V ? V + e * (int64_t)(9 * NN * NN) : nullptr, Pe + e * (3 * NN)};
+        VijEmit<NN> emit{V ? V + e * (int64_t)(9 * NN * NN) : nullptr, Pe + e * (3 * NN), transposed != 0};
         nodeRow<NN, NGP, MC, BLK>(sm, t, mp, V != nullptr, emit);
     }
 }
@@ -94,6 +99,59 @@ __global__ void updateCsrKernel(int64_t nNode, const int64_t* __restrict__ adjPt
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) data[base + i * 3 * deg + 3 * s + j] = acc[i * 3 + j];
+}
+
+// CSRGenerator.updateCSR on the TRANSPOSED internal scratch: one warp per node A accumulates its three CSR rows in shared
+// memory, element by element in ascending element order (== ascending COO index, the same summation order as
+// updateCsrKernel), reading 3 runs of ND contiguous doubles per incident element, and writes the rows once, coalesced.
+// rowBuf: 9 * maxDeg doubles per warp.
+template <int NN, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) rowGatherKernel(int64_t nNode, const int64_t* __restrict__ adjPtr, const int32_t* __restrict__ adj,
+                                                              const int64_t* __restrict__ incPtr, const int32_t* __restrict__ inc,
+                                                              const int32_t* __restrict__ conn, const double* __restrict__ Vt, double* __restrict__ data,
+                                                              int maxDeg) {
+    constexpr int ND = 3 * NN;
+    static_assert(NN <= 32, "one lane per element node");
+    extern __shared__ double rowBufAll[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t A = (int64_t)blockIdx.x * WARPS + warp;
+    if (A >= nNode) return;
+    double* buf = rowBufAll + (size_t)warp * 9 * maxDeg;
+    const int64_t s0 = adjPtr[A];
+    const int deg = (int)(adjPtr[A + 1] - s0);
+    const int rowLen = 3 * deg;
+    for (int i = lane; i < 3 * rowLen; i += 32) buf[i] = 0.0;
+    __syncwarp();
+    const int32_t* nb = adj + s0;
+    for (int64_t k = incPtr[A]; k < incPtr[A + 1]; ++k) {
+        const int32_t ea = inc[k];
+        const int64_t e = ea / NN;
+        const int a = ea % NN;
+        // slot of every node of the element inside A's sorted neighbour list (binary search, lane b < NN)
+        int slot = 0;
+        if (lane < NN) {
+            const int32_t B = conn[e * NN + lane];
+            int lo = 0, hi = deg - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (nb[mid] < B) lo = mid + 1; else hi = mid;
+            }
+            slot = lo;
+        }
+        const double* rows = Vt + e * (int64_t)(ND * ND) + (int64_t)(3 * a) * ND;
+#pragma unroll
+        for (int it = 0; it < (3 * ND + 31) / 32; ++it) {  // uniform trip count: every lane takes part in the shuffle
+            const int idx = it * 32 + lane;
+            const bool ok = idx < 3 * ND;
+            const int i = ok ? idx / ND : 0, c = ok ? idx - i * ND : 0;
+            const int b = c / 3, j = c - 3 * b;
+            const int s = __shfl_sync(0xffffffffu, slot, b);
+            if (ok) buf[i * rowLen + 3 * s + j] += rows[idx];
+        }
+        __syncwarp();
+    }
+    double* out = data + 9 * s0;
+    for (int i = lane; i < 3 * rowLen; i += 32) out[i] = buf[i];
 }
 
 // P[el] += Pe ; F[el] += |Pe| : per node, ascending element order.
