@@ -471,6 +471,75 @@ __device__ __forceinline__ void waitFlags(const volatile int* flag, int dep, boo
     EWB_SMEM_FENCE();
 }
 
+// Lean flush of one plane step for x-interior planes (1 <= ex, ex + 1 <= NX - 2, both planes owned by the chunk, no peer
+// buffer involved): the finished segments of the warp's (up to) four node columns go to the CSR value array.  For an interior
+// plane the 9 sub-row pieces of a node column (3 rows x {dx = -1, 0, +1}) start at  colPtr + m * (3 cy cz),  m = (dx + 1) + 3 i,
+// so one 64-bit base per column and an arithmetic progression replace the per-piece index arithmetic of flushPlane (which
+// stays in charge of the first / last planes of the box and of a chunk).  Plane ex: dx = 0 (seg0) and dx = +1 (segP) plus
+// P, F; plane ex + 1: dx = -1 (segM).  Every segment value read is cleared.
+template <int TY, int TZ>
+__device__ __forceinline__ void flushStepInterior(double* smem, const SweepArgs& A, int ex, int pyq, int pzq, int lane, int seg0, int segP,
+                                                  int segM, int pf, const int* colPart, const int* colCycz, const int* laneOff,
+                                                  int64_t totYZ, int NY, int NZ, int y0, int z0) {
+    constexpr int CS = 81;
+    const int64_t planeBase = 9 * (int64_t)(3 * ex - 1) * totYZ;
+    const int64_t nextPlane = 27 * totYZ;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const int ly_ = 2 * pyq + (cc >> 1), lz_ = 2 * pzq + (cc & 1);
+        if (ly_ >= TY || lz_ >= TZ) continue;  // warp uniform
+        const int col = ly_ * TZ + lz_;
+        const int lo = laneOff[col * 32 + lane];  // -1: lane >= 27, column outside the box, or neighbour (dy,dz) outside the box
+        const int stepE = 3 * colCycz[col];
+        const int cp = colPart[col];
+        if (lane < 27) {
+            double* s0 = smem + (seg0 + col * CS + lane);
+            double* sP = smem + (segP + col * CS + lane);
+            double* sM = smem + (segM + col * CS + lane);
+            double v0[3], vP[3], vM[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                v0[i] = s0[27 * i];
+                vP[i] = sP[27 * i];
+                vM[i] = sM[27 * i];
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                s0[27 * i] = 0.0;
+                sP[27 * i] = 0.0;
+                sM[27 * i] = 0.0;
+            }
+            if (lo >= 0) {
+                double* ptr = A.data + (planeBase + 27 * (int64_t)cp + lo);
+                double* ptrN = ptr + nextPlane;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    ptrN[(3 * i) * stepE] = vM[i];
+                    ptr[(3 * i + 1) * stepE] = v0[i];
+                    ptr[(3 * i + 2) * stepE] = vP[i];
+                }
+            }
+        }
+    }
+    // P, F of plane ex: lane = 3 cc + component
+    if (lane < 12) {
+        const int cc = lane / 3, c = lane - 3 * cc;
+        const int ly_ = 2 * pyq + (cc >> 1), lz_ = 2 * pzq + (cc & 1);
+        if (ly_ < TY && lz_ < TZ) {
+            const int col = ly_ * TZ + lz_;
+            double* pfp = smem + (pf + col * 6 + c);
+            const double pv = pfp[0], fv = pfp[3];
+            pfp[0] = 0.0;
+            pfp[3] = 0.0;
+            if (colCycz[col] != 0) {
+                const int64_t dof = 3 * ((((int64_t)ex * NY + (y0 + ly_)) * NZ) + (z0 + lz_)) + c;
+                A.P[dof] = pv;
+                A.F[dof] = fv;
+            }
+        }
+    }
+}
+
 // One warp per 2x2 element patch; number of warps == number of patches of the tile.
 template <int MC, bool TL, int TY, int TZ>
 __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweepKernel(const SweepArgs A) {
@@ -796,9 +865,13 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
         waitFlags(doneCnt, depD, hasD, 4 * (step + 1), A.failFlag, A.spinNs);
         EWB_ACC(4, tWF);
         EWB_TIC(tF);
-        if (loOwned) flushPlane(ex, -1, lo0, segP, pfLo);
-        if (hiOwned) flushPlane(ex + 1, segM, -1, -1, -1);
-        if (ex == exEnd && xb == NX) flushPlane(NX - 1, -1, hi0, -1, pfHi);  // last node plane: nothing above it
+        if (loOwned && hiOwned && ex >= 1 && ex + 1 <= NX - 2 && A.wantK && !A.accumulatePF) {
+            flushStepInterior<TY, TZ>(smem, A, ex, pyq, pzq, lane, lo0, segP, segM, pfLo, colPart, colCycz, laneOff, totYZ, NY, NZ, y0, z0);
+        } else {
+            if (loOwned) flushPlane(ex, -1, lo0, segP, pfLo);
+            if (hiOwned) flushPlane(ex + 1, segM, -1, -1, -1);
+            if (ex == exEnd && xb == NX) flushPlane(NX - 1, -1, hi0, -1, pfHi);  // last node plane: nothing above it
+        }
         EWB_SMEM_FENCE();
         __syncwarp();
         if (lane == 0) flushedCnt[p] = step + 1;
@@ -1174,9 +1247,13 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
         waitFlags(doneCnt, depD, hasD, 4 * (step + 1), A.failFlag, A.spinNs);
         EWB_ACC(4, tWF);
         EWB_TIC(tF);
-        if (loOwned) flushPlane(ex, -1, lo0, segP, pfLo);
-        if (hiOwned) flushPlane(ex + 1, segM, -1, -1, -1);
-        if (ex == exEnd && xb == NX) flushPlane(NX - 1, -1, hi0, -1, pfHi);  // last node plane: nothing above it
+        if (loOwned && hiOwned && ex >= 1 && ex + 1 <= NX - 2 && A.wantK && !A.accumulatePF) {
+            flushStepInterior<TY, TZ>(smem, A, ex, pyq, pzq, lane, lo0, segP, segM, pfLo, colPart, colCycz, laneOff, totYZ, NY, NZ, y0, z0);
+        } else {
+            if (loOwned) flushPlane(ex, -1, lo0, segP, pfLo);
+            if (hiOwned) flushPlane(ex + 1, segM, -1, -1, -1);
+            if (ex == exEnd && xb == NX) flushPlane(NX - 1, -1, hi0, -1, pfHi);  // last node plane: nothing above it
+        }
         EWB_SMEM_FENCE();
         __syncwarp();
         if (lane == 0) flushedCnt[p] = step + 1;

@@ -38,3 +38,8 @@ steps = full[:, :, 7].mean()
 print("cycles per plane step, mean over warps of full-tile CTAs:")
 for i, nme in [(j, names[j]) for j in (0, 8, 9, 10, 11, 1, 2, 3, 4, 5, 6)]:
     print(f"  {nme:14s} {full[:, :, i].mean() / steps:10.0f}   (per-warp min {full[:, :, i].mean(axis=0).min() / steps:8.0f}  max {full[:, :, i].mean(axis=0).max() / steps:8.0f})")
+
+# per-warp table (warp w runs on scheduler w % 4): cycles per plane step
+print("per-warp cycles per plane step (rows: warps; cols: wait_producer, wait_round, blocks, emission, wait_flush, flush, total)")
+for w in range(NW):
+    print(f"  warp {w:2d} smsp {w % 4}: " + " ".join(f"{full[:, w, i].mean() / steps:8.0f}" for i in (0, 1, 2, 3, 4, 5, 6)))
