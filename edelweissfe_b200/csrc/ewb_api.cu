@@ -491,6 +491,7 @@ int ewb_poll_status(ewb_plan* p, void* stream, double* pNewDT) {
     CUDA_TRY(cudaMemsetAsync(p->failFlag, 0, sizeof(int), st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (*p->failHost & 4) return fail(EWB_ERR_CUDA, "internal error: sweep kernel flag wait timed out (ordering bug)");
+    if (*p->failHost & 8) return fail(EWB_ERR_UNSUPPORTED, "element with non-positive Jacobian determinant (fused sweep needs w detJ > 0)");
     if (*p->failHost & 1) {
         if (pNewDT) *pNewDT = 0.5;
         g_err = "Von Mises Newton failed.";

@@ -72,6 +72,19 @@ struct RecLayout {
     static constexpr int PER_EL = 8 * RS;
 };
 
+// Linear-elastic producer/consumer kernel: the producers publish, per element, the scaled shape-function gradients already in
+// the mma fragment order, h_a = sqrt(w detJ) grad N_a (so that M = sum_gp h h^T needs one operand only), and S' = -sqrt(w detJ) sigma
+// (residual row P_a = sum_gp S' h_a).  A consumer lane then loads 6 + 12 doubles per element instead of 34, and the gradient
+// arithmetic moves from the three-consumer scheduler to the producers' schedulers.
+//   H[c][ks][row r = rowNode(a)][q]  at (2 c + ks) * KS + 4 r + q     (Gauss point 4 ks + q; one warp load = 32 consecutive doubles)
+//   S'[gp][6]                        at OFF_S + 6 gp
+// KS == 4, PER_EL == 8 (mod 16): the producer's stores (lane = element x Gauss point) hit 16 different banks per half-warp.
+struct RecLayoutH {
+    static constexpr int KS = 36;
+    static constexpr int OFF_S = 6 * KS;
+    static constexpr int PER_EL = OFF_S + 48;  // 264
+};
+
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
@@ -90,7 +103,7 @@ __device__ __forceinline__ int rowNode(int r) { return (0x67542310u >> (4 * r)) 
 // stg: the warp's staged nodal data [18 patch nodes][x,y,z,u0,u1,u2], already offset to this lane's element
 // (patch node of local node a = stg + (9 dx + 3 dy + dz) * 6).
 // LINEAR: stg holds the element's own 8 nodes [a][x,y,z,u0,u1,u2] instead of the 3x3x2 patch image.
-template <int MC, bool TL, bool LINEAR = false>
+template <int MC, bool TL, bool LINEAR = false, bool HREC = false>
 __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg, int gp, const MatParams& mp,
                                                   const double* __restrict__ state_ref, double* __restrict__ state_temp, int64_t cstride,
                                                   bool writeState, int* failFlag, long long* tsub = nullptr) {
@@ -138,8 +151,10 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
     double iJ[9];
     inv3(Jm, detJ, iJ);
     const double wd = w * detJ;
+    if constexpr (!HREC) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) rec[i] = iJ[i];
+        for (int i = 0; i < 9; ++i) rec[i] = iJ[i];
+    }
     EWB_SUB(1);
     // H[i][c] = du_i/dx_c = sum_r D[i][r] iJ[c][r]
     double H[9];
@@ -152,7 +167,25 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
         // Voigt 11,22,33,12,13,23 with engineering shear (_B3D8)
         const double de[6] = {H[0], H[4], H[8], H[1] + H[3], H[2] + H[6], H[5] + H[7]};
         double sg[6] = {st[0], st[1], st[2], st[3], st[4], st[5]};
-        if constexpr (MC == MC_LE) {
+        if constexpr (MC == MC_LE && HREC) {
+            static_assert(!HREC || (MC == MC_LE && !TL), "fragment-order records: linear elastic only");
+            hookeAdd(mp, de, sg);
+            if (!(wd > 0.0)) atomicOr(failFlag, 8);  // sqrt(w detJ): inverted element
+            const double sq = sqrt(wd);
+            const int ks = gp >> 2, q = gp & 3;
+            double* Hq = rec + ks * RecLayoutH::KS + q;
+            forNodes<8>([&](auto ic) {
+                constexpr int a = decltype(ic)::value;
+                constexpr int r = (0x67542310u >> (4 * a)) & 7;  // rowNode is an involution: row of node a
+                double d[3];
+                shapeDeriv<8, a>(xi, eta, zeta, d);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    Hq[2 * c * RecLayoutH::KS + 4 * r] = sq * (iJ[c * 3] * d[0] + iJ[c * 3 + 1] * d[1] + iJ[c * 3 + 2] * d[2]);
+            });
+#pragma unroll
+            for (int i = 0; i < 6; ++i) rec[RecLayoutH::OFF_S + 6 * gp + i] = -sq * sg[i];
+        } else if constexpr (MC == MC_LE) {
             hookeAdd(mp, de, sg);
             rec[R::C_CO] = wd;
         } else {
@@ -167,8 +200,10 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
 #pragma unroll
             for (int i = 0; i < 6; ++i) rec[R::C_X + i] = r.n[i];
         }
+        if constexpr (!HREC) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) rec[R::C_S + i] = -wd * sg[i];
+            for (int i = 0; i < 6; ++i) rec[R::C_S + i] = -wd * sg[i];
+        }
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             st[i] = sg[i];
@@ -368,6 +403,41 @@ __device__ __forceinline__ void elementTiles(const double* T, int lane, const do
         }
     }
     // reduce the residual row over the 4 lanes (Gauss-point pairs) of the row
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        Pr[i] += __shfl_xor_sync(0xffffffffu, Pr[i], 1);
+        Pr[i] += __shfl_xor_sync(0xffffffffu, Pr[i], 2);
+    }
+}
+
+// phase B from fragment-order records (RecLayoutH): M tiles and the residual row of one linear-elastic element
+__device__ __forceinline__ void elementTilesH(const double* T, int lane, bool wantK, TileAcc<MC_LE>& acc, double (&Pr)[3]) {
+    using H = RecLayoutH;
+    const int q = lane & 3;
+    double h[2][3];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) h[ks][c] = T[(2 * c + ks) * H::KS + lane];
+    auto& c = acc.c;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+    Pr[0] = Pr[1] = Pr[2] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        const double* S = T + H::OFF_S + 6 * (4 * ks + q);
+        Pr[0] += S[0] * h[ks][0] + S[3] * h[ks][1] + S[4] * h[ks][2];
+        Pr[1] += S[3] * h[ks][0] + S[1] * h[ks][1] + S[5] * h[ks][2];
+        Pr[2] += S[4] * h[ks][0] + S[5] * h[ks][1] + S[2] * h[ks][2];
+        if (wantK) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) dmma(c[i][j], h[ks][i], h[ks][j]);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         Pr[i] += __shfl_xor_sync(0xffffffffu, Pr[i], 1);
@@ -907,6 +977,8 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
     static_assert((TY & 1) == 1 && (TZ & 1) == 1, "tile edge must be odd (2x2 element patches)");
     static_assert(NW <= 32, "at most 32 patches per tile");
     constexpr bool COMPUTE_FIRST = (NW + NWP) <= 12;
+    constexpr bool HREC = (MC == MC_LE) && !TL;  // fragment-order records (RecLayoutH)
+    constexpr int PEL = HREC ? RecLayoutH::PER_EL : R::PER_EL;
 
     extern __shared__ double smem[];
     // Accumulator segments are addressed by OFFSETS (doubles) into `smem`, never by pointers that get swapped or selected:
@@ -923,7 +995,7 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
     volatile int* doneCnt = laneOff + NCOL * 32;  // [32] rounds completed per patch
     volatile int* flushedCnt = doneCnt + 32;      // [32] plane steps flushed per patch
     double* tables = smem + AL::TABLES;           // [2][NW][4][PER_EL] double-buffered Gauss-point records
-    double* stageAll = tables + (size_t)2 * NW * 4 * R::PER_EL;  // [NWP][2][108] nodal x,u of a patch's 3x3x2 nodes
+    double* stageAll = tables + (size_t)2 * NW * 4 * PEL;  // [NWP][2][108] nodal x,u of a patch's 3x3x2 nodes
     volatile int* producedCnt = reinterpret_cast<volatile int*>(stageAll + NWP * 216);  // [32] plane steps whose records are ready
     volatile int* consumedCnt = producedCnt + 32;                                      // [32] plane steps whose records are consumed
 
@@ -1030,12 +1102,12 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
             const int aey = y0 - 1 + apy, aez = z0 - 1 + apz;
             const bool aValid = aey >= 0 && aey < A.nY && aez >= 0 && aez < A.nZ && apy <= ny && apz <= nz;
             if (aValid) {
-                double* rec = tables + ((size_t)((step & 1) * NW + p) * 4 + ak) * R::PER_EL + agp * R::RS;
+                double* rec = tables + ((size_t)((step & 1) * NW + p) * 4 + ak) * PEL + (HREC ? 0 : agp * R::RS);
                 const int64_t e = ((int64_t)ex * A.nY + aey) * A.nZ + aez;
                 const int64_t off = e * 8 + agp;
                 const bool writeState = ex >= xa && apy >= 1 && apz >= 1;
-                gaussPointCompact<MC, TL>(rec, stage + ((ak >> 1) * 3 + (ak & 1)) * 6, agp, A.mp, A.stateRef + off, A.stateTemp + off, cstride,
-                                          writeState, A.failFlag);
+                gaussPointCompact<MC, TL, false, HREC>(rec, stage + ((ak >> 1) * 3 + (ak & 1)) * 6, agp, A.mp, A.stateRef + off, A.stateTemp + off,
+                                                       cstride, writeState, A.failFlag);
             }
             EWB_SMEM_FENCE();
             __syncwarp();
@@ -1176,7 +1248,7 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
         EWB_TIC(tWP);
         waitFlags(producedCnt, p, lane == 0, step + 1, A.failFlag, A.spinNs);
         EWB_ACC(0, tWP);
-        const double* wt = tables + (size_t)((step & 1) * NW + p) * 4 * R::PER_EL;
+        const double* wt = tables + (size_t)((step & 1) * NW + p) * 4 * PEL;
         // per-step accumulation bases of this lane (segments rotate every plane)
         int accBase[2];
 #pragma unroll
@@ -1192,7 +1264,16 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
             // ---- ordering: same-colour elements of different patches never share a node.  With registers to spare the
             // blocks are computed BEFORE the wait, so a fast warp's tensor work overlaps its neighbours' accumulation. ----
             EWB_TIC(tB);
-            if (COMPUTE_FIRST && valid) elementBlocks<MC>(wt + k * R::PER_EL, lane, dNl, A.mp, A.wantK != 0, K0, K1, Pr);
+            if constexpr (HREC) {
+                if (COMPUTE_FIRST && valid) {
+                    TileAcc<MC_LE> acc;
+                    elementTilesH(wt + k * PEL, lane, A.wantK != 0, acc, Pr);
+                    finishBlock<MC_LE>(acc, 0, A.mp, K0);
+                    finishBlock<MC_LE>(acc, 1, A.mp, K1);
+                }
+            } else {
+                if (COMPUTE_FIRST && valid) elementBlocks<MC>(wt + k * PEL, lane, dNl, A.mp, A.wantK != 0, K0, K1, Pr);
+            }
             if (COMPUTE_FIRST && k == 3) {  // all four elements' records are consumed: the producers may refill this buffer
                 __syncwarp();
                 if (lane == 0) consumedCnt[p] = step + 1;
@@ -1204,7 +1285,11 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
             EWB_ACC(1, tW);
             EWB_TIC(tB2);
             TileAcc<MC> tacc_;
-            if (!COMPUTE_FIRST && valid) elementTiles<MC>(wt + k * R::PER_EL, lane, dNl, A.mp, A.wantK != 0, tacc_, Pr);
+            if constexpr (HREC) {
+                if (!COMPUTE_FIRST && valid) elementTilesH(wt + k * PEL, lane, A.wantK != 0, tacc_, Pr);
+            } else {
+                if (!COMPUTE_FIRST && valid) elementTiles<MC>(wt + k * PEL, lane, dNl, A.mp, A.wantK != 0, tacc_, Pr);
+            }
             if (!COMPUTE_FIRST && k == 3) {  // all four elements' records are consumed: the producers may refill this buffer
                 __syncwarp();
                 if (lane == 0) consumedCnt[p] = step + 1;
@@ -1358,7 +1443,9 @@ struct SweepPlan {
         SweepArgs a;
         if (int rc = fillArgs<TY, TZ>(a, mp, b, failFlag, flags, st, NW_)) return rc;
         auto kern = sweepKernelPC<MC, TL, TY, TZ, NWP>;
-        const size_t smem = ((size_t)AccLayout<TY, TZ>::TABLES + (size_t)2 * NW_ * 4 * Rec::PER_EL + (size_t)NWP * 216 + 32) * sizeof(double);
+        constexpr int PEL = (MC == MC_LE && !TL) ? RecLayoutH::PER_EL : Rec::PER_EL;
+        const size_t smem = ((size_t)AccLayout<TY, TZ>::TABLES + (size_t)2 * NW_ * 4 * PEL + (size_t)NWP * 216 + 32) * sizeof(double);
+        if (smem > 232448) return EWB_ERR_UNSUPPORTED;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EWB_ERR_CUDA;
         const int64_t grid = (int64_t)a.tilesY * a.tilesZ * a.nChunks;
         kern<<<(unsigned)grid, (NW_ + NWP) * 32, smem, st>>>(a);
