@@ -1,4 +1,4 @@
-"""2-GPU parity of the slab-partitioned assembly (NCCL exchange + interface add) against the single-GPU
+"""2- and 4-GPU parity of the slab-partitioned assembly (NCCL exchange + interface add) against the single-GPU
 result.  Skipped on boxes with one GPU."""
 import os
 import socket
@@ -60,18 +60,18 @@ def _worker(rank, world, port_no, q, exchange):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 4])  # 4: ranks with BOTH neighbours (receive from below, store to the rank above)
 @pytest.mark.parametrize("exchange", ["peer", "nccl"])
-def test_two_gpu_slabs_match_single_gpu(exchange):
+def test_two_gpu_slabs_match_single_gpu(exchange, world):
     import torch
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     import scipy.sparse as sp
     import torch.multiprocessing as mp
 
     from edelweissfe_b200 import ElementAssembly
 
-    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port_no = _free_port()
