@@ -427,12 +427,14 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
     if (wantK) {
         V = b->vij;
         if (!V) {
-            if (!p->vijScratch) CUDA_TRY(cudaMalloc((void**)&p->vijScratch, (size_t)p->nEl * nd * nd * sizeof(double)));
+            // internal scratch: half-block layout (ewb_generic.cuh HalfLayout), 9 (NN/2 + 1) doubles (+ pad) per element node
+            const size_t se = (size_t)(p->nn == 8 ? ewb::HalfLayout<8>::SE : ewb::HalfLayout<20>::SE);
+            if (!p->vijScratch) CUDA_TRY(cudaMalloc((void**)&p->vijScratch, (size_t)p->nEl * se * sizeof(double)));
             V = p->vijScratch;
         }
     }
     const bool internalV = wantK && V == p->vijScratch;  // nobody else reads it: use the gather-friendly transposed layout
-    if (int rc = dispatchVij(p, mc, mp, b, V, p->peScratch, st, internalV ? 1 : 0)) return rc;
+    if (int rc = dispatchVij(p, mc, mp, b, V, p->peScratch, st, internalV ? 2 : 0)) return rc;
     {
         const int B = 256;
         const unsigned grid = (unsigned)((3 * p->nNode + B - 1) / B);
@@ -446,11 +448,11 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
         const size_t smem = (size_t)W * 9 * p->maxDeg * sizeof(double);
         const unsigned grid = (unsigned)((p->nNode + W - 1) / W);
         if (p->nn == 8) {
-            CUDA_TRY(cudaFuncSetAttribute(ewb::rowGatherKernel<8, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ewb::rowGatherKernel<8, W><<<grid, W * 32, smem, st>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, V, b->csr_data, p->maxDeg);
+            CUDA_TRY(cudaFuncSetAttribute(ewb::rowGatherHalfKernel<8, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ewb::rowGatherHalfKernel<8, W><<<grid, W * 32, smem, st>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, V, b->csr_data, p->maxDeg);
         } else {
-            CUDA_TRY(cudaFuncSetAttribute(ewb::rowGatherKernel<20, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ewb::rowGatherKernel<20, W><<<grid, W * 32, smem, st>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, V, b->csr_data, p->maxDeg);
+            CUDA_TRY(cudaFuncSetAttribute(ewb::rowGatherHalfKernel<20, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ewb::rowGatherHalfKernel<20, W><<<grid, W * 32, smem, st>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, V, b->csr_data, p->maxDeg);
         }
         LAUNCH_CHECK();
         return EWB_OK;

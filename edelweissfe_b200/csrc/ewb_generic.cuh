@@ -9,8 +9,48 @@
 
 namespace ewb {
 
+// Internal scratch of the arbitrary-mesh path ("half-block" layout): only the blocks the element loop computes are stored,
+// K[a][a + d] for d = 0 .. NN/2 (node pairs in circulant order, Ke is symmetric), 9 doubles each, contiguous per node a:
+//   S[e][a][d][3][3]  at  e * SE + a * SA + 9 d,   SA = 9 (NN/2 + 1) rounded up to even (16-byte aligned runs).
+// 55 % of the VIJ bytes (reference layout: 9 NN^2 doubles per element), written as 16-byte stores of runs that are contiguous
+// per thread; rowGatherHalfKernel reads block (a, b) either directly (d = b - a < nb(a)) or as the transpose of (b, a).
+template <int NN>
+struct HalfLayout {
+    static constexpr int HALF = NN / 2, NB = HALF + 1;
+    static constexpr int SA = (NB * 9 + 1) & ~1;
+    static constexpr int SE = NN * SA;
+};
+
+template <int NN>
+struct HalfEmit {
+    static constexpr bool HALF = true;
+    double* S;   // element slice [SE]
+    double* Pe;  // element slice [3 NN]
+    __device__ __forceinline__ void residual(int a, const double P[3]) const {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Pe[3 * a + i] = P[i];
+    }
+    __device__ __forceinline__ void block(int, int, const double*) const {}
+    template <int BLK>
+    __device__ __forceinline__ void pass(int a, int ps, const double (&out)[BLK * 9 + 1]) const {
+        using HL = HalfLayout<NN>;
+        constexpr int NPASS = (HL::NB + BLK - 1) / BLK;
+        static_assert(NPASS == 1 || (BLK * 9) % 2 == 0, "runs of later passes must stay 16-byte aligned");
+        double2* dst = reinterpret_cast<double2*>(S + a * HL::SA + ps * (BLK * 9));
+        // doubles of this pass: blocks d = ps*BLK .. min(NB, (ps+1)*BLK) - 1, rounded up to a pair (the pad slot exists in SA)
+        const int nBlk = min(BLK, HL::NB - ps * BLK);
+        const int nPair = (nBlk * 9 + 1) >> 1;
+#pragma unroll
+        for (int q = 0; q < (BLK * 9 + 1) / 2; ++q)
+            if (q < nPair) dst[q] = make_double2(out[2 * q], out[2 * q + 1]);
+    }
+};
+
 template <int NN>
 struct VijEmit {
+    static constexpr bool HALF = false;
+    template <int BLK>
+    __device__ __forceinline__ void pass(int, int, const double (&)[BLK * 9 + 1]) const {}
     static constexpr int ND = 3 * NN;
     double* V;   // element slice [ND*ND] or nullptr
     double* Pe;  // element slice [ND]
@@ -53,8 +93,13 @@ __global__ void __launch_bounds__(T* E) computeElementsVijKernel(int64_t nEl, co
     }
     __syncthreads();
     if (active && t < NN) {
-        VijEmit<NN> emit{V ? V + e * (int64_t)(9 * NN * NN) : nullptr, Pe + e * (3 * NN), transposed != 0};
-        nodeRow<NN, NGP, MC, BLK>(sm, t, mp, V != nullptr, emit);
+        if (transposed == 2) {  // internal half-block scratch
+            HalfEmit<NN> emit{V + e * (int64_t)HalfLayout<NN>::SE, Pe + e * (3 * NN)};
+            nodeRow<NN, NGP, MC, BLK>(sm, t, mp, V != nullptr, emit);
+        } else {
+            VijEmit<NN> emit{V ? V + e * (int64_t)(9 * NN * NN) : nullptr, Pe + e * (3 * NN), transposed != 0};
+            nodeRow<NN, NGP, MC, BLK>(sm, t, mp, V != nullptr, emit);
+        }
     }
 }
 
@@ -147,6 +192,72 @@ __global__ void __launch_bounds__(WARPS * 32) rowGatherKernel(int64_t nNode, con
             const int b = c / 3, j = c - 3 * b;
             const int s = __shfl_sync(0xffffffffu, slot, b);
             if (ok) buf[i * rowLen + 3 * s + j] += rows[idx];
+        }
+        __syncwarp();
+    }
+    double* out = data + 9 * s0;
+    for (int i = lane; i < 3 * rowLen; i += 32) out[i] = buf[i];
+}
+
+// CSRGenerator.updateCSR on the half-block scratch (HalfLayout): one warp per node A, lane b < NN owns the block (a, b) of the
+// incident element (e, a) — stored as K[a][a+d] if d = b - a (mod NN) < nb(a), else as the transpose of K[b][b+d'] — and adds it
+// to A's three CSR rows in shared memory.  Elements are visited in ascending order (== ascending COO index, the reference's
+// summation order); the next element's block travels while the current one is added.
+template <int NN, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) rowGatherHalfKernel(int64_t nNode, const int64_t* __restrict__ adjPtr, const int32_t* __restrict__ adj,
+                                                                  const int64_t* __restrict__ incPtr, const int32_t* __restrict__ inc,
+                                                                  const int32_t* __restrict__ conn, const double* __restrict__ S, double* __restrict__ data,
+                                                                  int maxDeg) {
+    using HL = HalfLayout<NN>;
+    static_assert(NN <= 32, "one lane per element node");
+    extern __shared__ double rowBufAll[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t A = (int64_t)blockIdx.x * WARPS + warp;
+    if (A >= nNode) return;
+    double* buf = rowBufAll + (size_t)warp * 9 * maxDeg;
+    const int64_t s0 = adjPtr[A];
+    const int deg = (int)(adjPtr[A + 1] - s0);
+    const int rowLen = 3 * deg;
+    for (int i = lane; i < 3 * rowLen; i += 32) buf[i] = 0.0;
+    const int32_t* nb = adj + s0;
+    const int64_t k0 = incPtr[A], k1 = incPtr[A + 1];
+    // fetch: this lane's block of incident element k (registers) and its slot in A's sorted neighbour list
+    auto fetch = [&](int64_t k, double (&v)[9], int& slot, bool& direct) {
+        const int32_t ea = inc[k];
+        const int64_t e = ea / NN;
+        const int a = ea % NN;
+        const int b = lane;
+        int d = b - a;
+        if (d < 0) d += NN;
+        direct = d < HL::HALF + (a < HL::HALF ? 1 : 0);
+        const double* src = S + e * (int64_t)HL::SE + (direct ? a * HL::SA + d * 9 : b * HL::SA + (NN - d) * 9);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) v[i] = src[i];
+        const int32_t B = conn[e * NN + b];
+        int lo = 0, hi = deg - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (nb[mid] < B) lo = mid + 1; else hi = mid;
+        }
+        slot = lo;
+    };
+    double v[9], w[9];
+    int slot = 0, slotN = 0;
+    bool direct = true, directN = true;
+    if (lane < NN && k0 < k1) fetch(k0, v, slot, direct);
+    __syncwarp();
+    for (int64_t k = k0; k < k1; ++k) {
+        if (lane < NN) {
+            if (k + 1 < k1) fetch(k + 1, w, slotN, directN);
+            double* dst = buf + 3 * slot;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) dst[i * rowLen + j] += direct ? v[i * 3 + j] : v[j * 3 + i];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) v[i] = w[i];
+            slot = slotN;
+            direct = directN;
         }
         __syncwarp();
     }

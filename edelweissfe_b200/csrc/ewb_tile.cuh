@@ -513,6 +513,26 @@ __device__ __forceinline__ void nodeRow(const double* sm, int a, const MatParams
             }
         }
 
+        if constexpr (Emit::HALF) {
+            // half-block scratch: the thread's blocks (a, a + d) of this pass are one contiguous run of BLK * 9 doubles
+            double out[BLK * 9 + 1];
+            out[BLK * 9] = 0.0;
+#pragma unroll
+            for (int k = 0; k < BLK; ++k) {
+                if constexpr (MC == MC_LE) {
+                    const double* M = acc[k];
+                    const double tr = mp.G * (M[0] + M[4] + M[8]);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) out[k * 9 + i * 3 + j] = mp.lambda * M[i * 3 + j] + mp.G * M[j * 3 + i] + (i == j ? tr : 0.0);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) out[k * 9 + i] = acc[k][i];
+                }
+            }
+            emit.template pass<BLK>(a, pass, out);
+        } else {
 #pragma unroll
         for (int k = 0; k < BLK; ++k) {
             const int d = pass * BLK + k;
@@ -537,6 +557,7 @@ __device__ __forceinline__ void nodeRow(const double* sm, int a, const MatParams
                     emit.block(b, a, Kt);
                 }
             }
+        }
         }
     }
 }
