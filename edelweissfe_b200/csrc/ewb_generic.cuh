@@ -73,7 +73,7 @@ struct VijEmit {
 
 // T threads cooperate on one element (T >= NGP and T >= NN), E elements per CTA.
 template <int NN, int NGP, int MC, bool TL, int T, int E, int BLK>
-__global__ void __launch_bounds__(T* E) computeElementsVijKernel(int64_t nEl, const int32_t* __restrict__ conn, const double* __restrict__ coords,
+__global__ void __launch_bounds__(T* E, (NN == 20 ? 3 : 1)) computeElementsVijKernel(int64_t nEl, const int32_t* __restrict__ conn, const double* __restrict__ coords,
                                                                 const double* __restrict__ U, const double* __restrict__ dU,
                                                                 const double* __restrict__ stateRef, double* __restrict__ stateTemp,
                                                                 double* __restrict__ V, double* __restrict__ Pe, MatParams mp, int* failFlag,

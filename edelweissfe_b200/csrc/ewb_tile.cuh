@@ -39,7 +39,7 @@ struct TileLayout {
     // (tensor order xx,yy,zz,xy,xz,yz), [10..18] F (only W_b needs it in phase B)
     // hypo-elastic TL: [10..18] F, [20..25] w detJ mu' (F F^T) (xx,yy,zz,xy,xz,yz); Q holds f_a = F grad N_a, R holds p_a = F N grad N_a
     static constexpr bool HASR = (MC == MC_TLV);
-    static constexpr int NCO = isHypoTL(MC) ? 26 : 20;
+    static constexpr int NCO = isHypoTL(MC) ? 26 : (MC == MC_NH ? 20 : 11);  // LE / VM use slots 0..9; odd stride: conflict-free stores
     static constexpr int OFF_G = 0;
     static constexpr int OFF_Q = OFF_G + NGP * GST;
     static constexpr int OFF_R = OFF_Q + (HASQ ? NGP * GST : 0);
