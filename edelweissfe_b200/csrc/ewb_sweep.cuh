@@ -267,7 +267,8 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
 template <int MC> struct TileAcc;
 template <> struct TileAcc<MC_LE> { double c[3][3][2]; };
 template <> struct TileAcc<MC_VM> { double c1[3][3][2], c2[3][3][2]; bool elastic; };  // elastic: all 8 Gauss points of the element stayed elastic
-template <> struct TileAcc<MC_NH> { double c1[3][3][2], c2[3][3][2], d0[3][2]; };
+// NH: c1[i][i] holds the merged diagonal tile sum (c1 + c2) n_i n_i (K_ii needs only their sum), c2[i][i] is unused; d0 = sum_i c0 g_i g_i
+template <> struct TileAcc<MC_NH> { double c1[3][3][2], c2[3][3][2], d0[2]; };
 
 template <int MC>
 __device__ __forceinline__ void elementTiles(const double* T, int lane, const double (&dNl)[2][3], const MatParams& mp, bool wantK,
@@ -356,9 +357,9 @@ __device__ __forceinline__ void elementTiles(const double* T, int lane, const do
         auto& c1 = acc.c1;
         auto& c2 = acc.c2;
         auto& d0 = acc.d0;
+        d0[0] = d0[1] = 0.0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            d0[i][0] = d0[i][1] = 0.0;
 #pragma unroll
             for (int j = 0; j < 3; ++j) c1[i][j][0] = c1[i][j][1] = c2[i][j][0] = c2[i][j][1] = 0.0;
         }
@@ -380,11 +381,15 @@ __device__ __forceinline__ void elementTiles(const double* T, int lane, const do
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const double a1 = k1 * nv[i], a2 = k2 * nv[i];
-                    dmma(d0[i], k0 * g[ks][i], g[ks][i]);
+                    dmma(d0, k0 * g[ks][i], g[ks][i]);
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        dmma(c1[i][j], a1, nv[j]);
-                        dmma(c2[i][j], a2, nv[j]);
+                        if (i == j) {
+                            dmma(c1[i][i], a1 + a2, nv[i]);
+                        } else {
+                            dmma(c1[i][j], a1, nv[j]);
+                            dmma(c2[i][j], a2, nv[j]);
+                        }
                     }
                 }
                 if (wb) {  // W_b: + c4 (f_a n_b^T + n_a f_b^T), f = F grad N
@@ -477,11 +482,11 @@ __device__ __forceinline__ void finishBlock(const TileAcc<MC>& acc, int t, const
                 for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = acc.c1[i][j][t] + acc.c2[j][i][t] + (i == j ? tr : 0.0);
         }
     } else {
-        const double tr = acc.d0[0][t] + acc.d0[1][t] + acc.d0[2][t];
+        const double tr = acc.d0[t];
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = acc.c1[i][j][t] + acc.c2[j][i][t] + (i == j ? tr : 0.0);
+            for (int j = 0; j < 3; ++j) Kt[i * 3 + j] = i == j ? acc.c1[i][i][t] + tr : acc.c1[i][j][t] + acc.c2[j][i][t];
     }
 }
 

@@ -16,8 +16,21 @@ from edelweissfe_b200 import ElementAssembly, box_mesh  # noqa: E402
 
 n = (100, 100, 100)
 coords, conn = box_mesh(*n, lX=100.0, lY=100.0, lZ=100.0)
-asm = ElementAssembly("C3D8", conn, coords, "linearelastic", [2.1e4, 0.22], box=n)
-dU = 1e-3 * torch.randn(asm.nDof, dtype=torch.float64)
+WHAT = os.environ.get("EWB_WHAT", "le")  # le | vm | nh   (vm / nh: single-role kernel, EWB_NW=12)
+if WHAT == "vm":
+    asm = ElementAssembly("C3D8", conn, coords, "vonmises", [2.1e4, 0.22, 355.0, 1000.0, 200.0, 1400.0], box=n)
+    import numpy as np
+    G = 2.1e4 / (2 * 1.22)
+    gmax = 2.0 * 355.0 / (np.sqrt(3.0) * G)
+    d = 1e-6 * np.random.default_rng(0).standard_normal(asm.nDof)
+    d[0::3] += 0.5 * gmax * coords[:, 1] ** 2 / 100.0
+    dU = torch.as_tensor(d)
+elif WHAT == "nh":
+    asm = ElementAssembly("C3D8TL", conn, coords, "neohookewa", [91304.34783, 100000.0], box=n)
+    dU = 1e-2 * torch.randn(asm.nDof, dtype=torch.float64)
+else:
+    asm = ElementAssembly("C3D8", conn, coords, "linearelastic", [2.1e4, 0.22], box=n)
+    dU = 1e-3 * torch.randn(asm.nDof, dtype=torch.float64)
 asm.U.copy_(dU)
 asm.dU.copy_(dU)
 for _ in range(3):
