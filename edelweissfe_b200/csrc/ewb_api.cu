@@ -132,8 +132,8 @@ int dispatchVij(ewb_plan* p, int mc, const ewb::MatParams& mp, const ewb_buffers
         if (mc == ewb::MC_TLE) return launchVij<8, 8, ewb::MC_TLE, true, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);  // element.py:415-425
         if (mc == ewb::MC_TLV) return launchVij<8, 8, ewb::MC_TLV, true, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
     } else if (p->elType == EWB_C3D20) {
-        if (mc == ewb::MC_LE) return launchVij<20, 27, ewb::MC_LE, false, 32, 4, 6>(p, mp, b, V, Pe, st, transposed);
-        if (mc == ewb::MC_VM) return launchVij<20, 27, ewb::MC_VM, false, 32, 4, 6>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_LE) return launchVij<20, 27, ewb::MC_LE, false, 32, 4, 4>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_VM) return launchVij<20, 27, ewb::MC_VM, false, 32, 4, 4>(p, mp, b, V, Pe, st, transposed);
     } else if (p->elType == EWB_C3D8R) {
         if (mc == ewb::MC_LE) return launchVij<8, 1, ewb::MC_LE, false, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
         if (mc == ewb::MC_VM) return launchVij<8, 1, ewb::MC_VM, false, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
@@ -141,8 +141,8 @@ int dispatchVij(ewb_plan* p, int mc, const ewb::MatParams& mp, const ewb_buffers
         if (mc == ewb::MC_LE) return launchVij<8, 27, ewb::MC_LE, false, 32, 4, 5>(p, mp, b, V, Pe, st, transposed);
         if (mc == ewb::MC_VM) return launchVij<8, 27, ewb::MC_VM, false, 32, 4, 5>(p, mp, b, V, Pe, st, transposed);
     } else if (p->elType == EWB_C3D20R) {
-        if (mc == ewb::MC_LE) return launchVij<20, 8, ewb::MC_LE, false, 32, 4, 6>(p, mp, b, V, Pe, st, transposed);
-        if (mc == ewb::MC_VM) return launchVij<20, 8, ewb::MC_VM, false, 32, 4, 6>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_LE) return launchVij<20, 8, ewb::MC_LE, false, 32, 4, 4>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_VM) return launchVij<20, 8, ewb::MC_VM, false, 32, 4, 4>(p, mp, b, V, Pe, st, transposed);
     }
     return fail(EWB_ERR_UNSUPPORTED, "element/material combination not implemented");
 }

@@ -71,6 +71,79 @@ struct VijEmit {
     }
 };
 
+// Phase B of a linear-elastic 20-node element on the FP64 tensor pipe (one warp per element, half-block scratch).
+// ncu of the scalar form (nodeRow): the LSU data pipe is 85 % busy — every 9 FMA of a block need 3 shared-memory loads of
+// grad N_b, 62 % of all shared-memory wavefronts — while the FP64 pipe runs at 38 %.  As a (60 x 27) x (27 x 60) product on
+// 8x8x4 tiles the operands are reused across the 9 component pairs: 7 loads per 9 DMMA (2304 FMA), 6 x fewer wavefronts.
+// Node tiles ta <= tb of 8 rows / columns (20 nodes padded to 24, 27 Gauss points to 28); lane (r, q) ends with the two
+// complete 3x3 blocks (a = 8 ta + r, b = 8 tb + 2 q + t) and stores those with a <= b into the circulant half layout
+// (directly as K[a][a+d] if d = b - a < nb(a), else transposed under b).
+__device__ __forceinline__ void dmmaG(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <int NGP>
+__device__ __forceinline__ void phaseBDmma20LE(const double* sm, int lane, const MatParams& mp, double* Se) {
+    constexpr int NN = 20;
+    using L = TileLayout<NN, NGP, MC_LE>;
+    using HL = HalfLayout<NN>;
+    constexpr int KSTEPS = (NGP + 3) / 4;
+    const double* G = sm + L::OFF_G;
+    const double* CO = sm + L::OFF_CO;
+    const int r = lane >> 2, q = lane & 3;
+#pragma unroll 1
+    for (int ta = 0; ta < 3; ++ta) {
+        const int a = 8 * ta + r;
+        const bool aok = a < NN;
+#pragma unroll 1
+        for (int tb = ta; tb < 3; ++tb) {
+            const int bn = 8 * tb + r;  // node of this lane's B-fragment column
+            const bool bok = bn < NN;
+            double c[3][3][2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                const int gp = 4 * ks + q;
+                const bool gok = gp < NGP;
+                const double* Gg = G + (gok ? gp : 0) * L::GST;
+                const double w = gok ? CO[gp * L::NCO] : 0.0;
+                double A[3], B[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    A[i] = aok ? w * Gg[a * 3 + i] : 0.0;
+                    B[i] = (bok && gok) ? Gg[bn * 3 + i] : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) dmmaG(c[i][j], A[i], B[j]);
+            }
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int b = 8 * tb + 2 * q + t;
+                if (aok && b < NN && a <= b) {
+                    double K[9];
+                    const double tr = mp.G * (c[0][0][t] + c[1][1][t] + c[2][2][t]);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) K[i * 3 + j] = mp.lambda * c[i][j][t] + mp.G * c[j][i][t] + (i == j ? tr : 0.0);
+                    const int d = b - a;
+                    const bool direct = d < HL::HALF + (a < HL::HALF ? 1 : 0);
+                    double* dst = Se + (direct ? a * HL::SA + d * 9 : b * HL::SA + (NN - d) * 9);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) dst[i * 3 + j] = direct ? K[i * 3 + j] : K[j * 3 + i];
+                }
+            }
+        }
+    }
+}
+
 // T threads cooperate on one element (T >= NGP and T >= NN), E elements per CTA.
 template <int NN, int NGP, int MC, bool TL, int T, int E, int BLK>
 __global__ void __launch_bounds__(T* E, (NN == 20 ? 3 : 1)) computeElementsVijKernel(int64_t nEl, const int32_t* __restrict__ conn, const double* __restrict__ coords,
@@ -84,6 +157,11 @@ __global__ void __launch_bounds__(T* E, (NN == 20 ? 3 : 1)) computeElementsVijKe
     const int64_t e = (int64_t)blockIdx.x * E + el;
     double* sm = smem + el * L::PER_EL;
     const bool active = e < nEl;
+    if (active && t < NGP) {  // the Gauss-point state is needed after the first barrier: pull it into L2 now
+        const double* sp = stateRef + e * NGP + t;
+#pragma unroll
+        for (int c = 0; c < 12 + matStateCount(MC); ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + c * (nEl * NGP)));
+    }
     if (active) stageNodes<NN, NGP, MC, T>(sm, conn + e * NN, coords, U, dU, t);
     __syncthreads();
     if (active && t < NGP) {
@@ -92,13 +170,30 @@ __global__ void __launch_bounds__(T* E, (NN == 20 ? 3 : 1)) computeElementsVijKe
         gaussPoint<NN, NGP, MC, TL>(sm, t, mp, stateRef + off, stateTemp + off, cstride, true, failFlag);
     }
     __syncthreads();
-    if (active && t < NN) {
-        if (transposed == 2) {  // internal half-block scratch
-            HalfEmit<NN> emit{V + e * (int64_t)HalfLayout<NN>::SE, Pe + e * (3 * NN)};
-            nodeRow<NN, NGP, MC, BLK>(sm, t, mp, V != nullptr, emit);
-        } else {
-            VijEmit<NN> emit{V ? V + e * (int64_t)(9 * NN * NN) : nullptr, Pe + e * (3 * NN), transposed != 0};
-            nodeRow<NN, NGP, MC, BLK>(sm, t, mp, V != nullptr, emit);
+    // phase B work items: (node row a, pass of BLK circulant blocks), spread over the T threads of the element
+    constexpr int NPASS = (NN / 2 + 1 + BLK - 1) / BLK;
+    if constexpr (NN == 20 && MC == MC_LE && T == 32) {
+        if (active && transposed == 2 && V != nullptr) {  // warp-uniform: one warp per element
+            if (t < NN) {
+                HalfEmit<NN> emit{V + e * (int64_t)HalfLayout<NN>::SE, Pe + e * (3 * NN)};
+                nodeRow<NN, NGP, MC, BLK>(sm, t, mp, false, emit);  // residual row only
+            }
+            __syncwarp();
+            phaseBDmma20LE<NGP>(sm, t, mp, V + e * (int64_t)HalfLayout<NN>::SE);
+            return;
+        }
+    }
+    if (active) {
+#pragma unroll 1
+        for (int it = t; it < NN * NPASS; it += T) {
+            const int a = it % NN, ps = it / NN;
+            if (transposed == 2) {  // internal half-block scratch
+                HalfEmit<NN> emit{V + e * (int64_t)HalfLayout<NN>::SE, Pe + e * (3 * NN)};
+                nodeRow<NN, NGP, MC, BLK>(sm, a, mp, V != nullptr, emit, ps, ps + 1, ps == 0);
+            } else {
+                VijEmit<NN> emit{V ? V + e * (int64_t)(9 * NN * NN) : nullptr, Pe + e * (3 * NN), transposed != 0};
+                nodeRow<NN, NGP, MC, BLK>(sm, a, mp, V != nullptr, emit, ps, ps + 1, ps == 0);
+            }
         }
     }
 }

@@ -310,7 +310,8 @@ __device__ __forceinline__ void gaussPoint(double* sm, int gp, const MatParams& 
 // Emit must provide:  void residual(int a, const double P[3]);
 //                     void block(int a, int b, const double K[9]);   // K[i*3+j] = Ke[3a+i][3b+j]
 template <int NN, int NGP, int MC, int BLK, class Emit>
-__device__ __forceinline__ void nodeRow(const double* sm, int a, const MatParams& mp, bool wantK, Emit& emit) {
+__device__ __forceinline__ void nodeRow(const double* sm, int a, const MatParams& mp, bool wantK, Emit& emit, int passBegin = 0,
+                                        int passEnd = 1 << 30, bool doResidual = true) {
     using L = TileLayout<NN, NGP, MC>;
     constexpr int HALF = NN / 2;
     const double* G = sm + L::OFF_G;
@@ -320,7 +321,7 @@ __device__ __forceinline__ void nodeRow(const double* sm, int a, const MatParams
     constexpr int NPASS = (HALF + 1 + BLK - 1) / BLK;
 
     // residual row: P_a = sum_gp (-w detJ S) v_a, v = grad N_a (small strain) or n_a (TL)
-    {
+    if (doResidual) {
         double P[3] = {0, 0, 0};
         for (int gp = 0; gp < NGP; ++gp) {
             const double* v = (MC == MC_NH ? Q : G) + gp * L::GST + a * 3;
@@ -344,7 +345,7 @@ __device__ __forceinline__ void nodeRow(const double* sm, int a, const MatParams
     if (!wantK) return;
 
 #pragma unroll 1
-    for (int pass = 0; pass < NPASS; ++pass) {
+    for (int pass = passBegin; pass < min(passEnd, NPASS); ++pass) {
         double acc[BLK][9];
 #pragma unroll
         for (int k = 0; k < BLK; ++k)
