@@ -62,6 +62,7 @@ SYMBOLS = {
     "ewb_plan_slot_map": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "ewb_plan_set_box": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64]),
     "ewb_plan_is_box": (C.c_int, [_P]),
+    "ewb_plan_set_gather_order": (C.c_int, [_P, _P]),
     "ewb_assemble": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(EwbBuffers), C.POINTER(C.c_double), C.c_double, C.c_int, _P]),
     "ewb_poll_status": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
     "ewb_compute_elements_vij": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(EwbBuffers), _P, C.c_int, _P]),

@@ -13,6 +13,7 @@ Reference interfaces mirrored (paths below /root/reference/edelweissfe/):
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -31,6 +32,25 @@ class CutbackRequest(Exception):
 
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def morton_order(coords: np.ndarray) -> np.ndarray:
+    """Permutation of the nodes along a Z-order curve of their coordinates (10 bits per axis): spatially close nodes
+    become neighbours in the visiting order of the row gather (ewb_plan_set_gather_order)."""
+    x = np.asarray(coords, dtype=np.float64)
+    lo, hi = x.min(axis=0), x.max(axis=0)
+    span = np.where(hi > lo, hi - lo, 1.0)
+    q = np.minimum(((x - lo) / span * 1024.0).astype(np.uint64), 1023)
+
+    def spread(v):  # 10 bits -> every third bit
+        v = (v | (v << 16)) & np.uint64(0x030000FF)
+        v = (v | (v << 8)) & np.uint64(0x0300F00F)
+        v = (v | (v << 4)) & np.uint64(0x030C30C3)
+        v = (v | (v << 2)) & np.uint64(0x09249249)
+        return v
+
+    key = (spread(q[:, 0]) << np.uint64(2)) | (spread(q[:, 1]) << np.uint64(1)) | spread(q[:, 2])
+    return np.ascontiguousarray(np.argsort(key, kind="stable").astype(np.int32))
 
 
 class ElementAssembly:
@@ -61,6 +81,12 @@ class ElementAssembly:
         self.plan = plan
         if box is not None:
             check(self.lib.ewb_plan_set_box(self.plan, int(box[0]), int(box[1]), int(box[2])))
+        # arbitrary-mesh path: the row gather visits the nodes in Morton order of the coordinates (locality hint, results unchanged)
+        # (measured on B200: DRAM reads of the gather 16.7 -> 9.7 GB for C3D20 100x100x50, but the kernel is latency bound and
+        # does not get faster, so the hint is off unless EWB_GATHER_ORDER=morton)
+        if os.environ.get("EWB_GATHER_ORDER", "none") == "morton":
+            order = morton_order(coords_t.detach().cpu().numpy())
+            check(self.lib.ewb_plan_set_gather_order(self.plan, order.ctypes.data_as(C.c_void_p)))
         self.nnz = self.lib.ewb_plan_nnz(self.plan)
         f64 = dict(dtype=torch.float64, device=self.device)
         self.coords = coords_t.to(**f64).contiguous()

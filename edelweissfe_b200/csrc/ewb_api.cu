@@ -58,6 +58,8 @@ struct ewb_plan {
     int64_t* incPtr = nullptr;   // [nNode+1]  node -> incident (element*nn + localNode), ascending element
     int32_t* inc = nullptr;
     int maxDeg = 0;              // largest node degree (row-gather shared-memory size)
+    unsigned char* gatherSlots = nullptr;  // [nInc][nn] element-to-CSR-slot map of the row gather (built at first use, maxDeg <= 255)
+    int32_t* gatherOrder = nullptr;  // optional [nNode] visiting order of the row gather (ewb_plan_set_gather_order)
     int* failFlag = nullptr;     // device status word
     int* failHost = nullptr;     // pinned mirror
     double* peScratch = nullptr; // [nEl][3nn] per-element residual (generic path)
@@ -226,7 +228,7 @@ void ewb_plan_destroy(ewb_plan* p) {
     if (!p) return;
     cudaSetDevice(p->device);
     cudaFree(p->conn); cudaFree(p->adjPtr); cudaFree(p->adj); cudaFree(p->incPtr); cudaFree(p->inc);
-    cudaFree(p->failFlag); cudaFree(p->peScratch); cudaFree(p->vijScratch);
+    cudaFree(p->failFlag); cudaFree(p->peScratch); cudaFree(p->vijScratch); cudaFree(p->gatherOrder); cudaFree(p->gatherSlots);
     if (p->failHost) cudaFreeHost(p->failHost);
     p->sweep.release();
     p->staged.release();
@@ -368,6 +370,25 @@ int ewb_plan_set_box(ewb_plan* p, int64_t nX, int64_t nY, int64_t nZ) {
     return EWB_OK;
 }
 
+int ewb_plan_set_gather_order(ewb_plan* p, const int32_t* order_host) {
+    if (!p) return fail(EWB_ERR_ARG, "null plan");
+    CUDA_TRY(cudaSetDevice(p->device));
+    if (!order_host) {
+        cudaFree(p->gatherOrder);
+        p->gatherOrder = nullptr;
+        return EWB_OK;
+    }
+    std::vector<char> seen((size_t)p->nNode, 0);
+    for (int64_t i = 0; i < p->nNode; ++i) {
+        const int32_t v = order_host[i];
+        if (v < 0 || v >= p->nNode || seen[v]) return fail(EWB_ERR_ARG, "ewb_plan_set_gather_order: not a permutation of the nodes");
+        seen[v] = 1;
+    }
+    if (!p->gatherOrder) CUDA_TRY(cudaMalloc((void**)&p->gatherOrder, (size_t)p->nNode * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpy(p->gatherOrder, order_host, (size_t)p->nNode * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return EWB_OK;
+}
+
 int ewb_compute_elements_vij(ewb_plan* p, int material, const double* props, int n_props, const ewb_buffers* b, double* pe_dev, int flags,
                              void* stream) {
     if (!p || !b || !props || !pe_dev) return fail(EWB_ERR_ARG, "ewb_compute_elements_vij: bad arguments");
@@ -445,14 +466,22 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
     }
     if (wantK && internalV) {
         constexpr int W = 8;
+        if (!p->gatherSlots && p->maxDeg <= 255) {
+            const int64_t nInc = p->nEl * p->nn;
+            CUDA_TRY(cudaMalloc((void**)&p->gatherSlots, (size_t)nInc * p->nn));
+            const unsigned g = (unsigned)((p->nNode + 7) / 8);
+            if (p->nn == 8) ewb::gatherSlotKernel<8><<<g, 256, 0, st>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, p->gatherSlots);
+            else ewb::gatherSlotKernel<20><<<g, 256, 0, st>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, p->gatherSlots);
+            LAUNCH_CHECK();
+        }
         const size_t smem = (size_t)W * 9 * p->maxDeg * sizeof(double);
         const unsigned grid = (unsigned)((p->nNode + W - 1) / W);
         if (p->nn == 8) {
             CUDA_TRY(cudaFuncSetAttribute(ewb::rowGatherHalfKernel<8, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ewb::rowGatherHalfKernel<8, W><<<grid, W * 32, smem, st>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, V, b->csr_data, p->maxDeg);
+            ewb::rowGatherHalfKernel<8, W><<<grid, W * 32, smem, st>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, V, b->csr_data, p->maxDeg, p->gatherOrder, p->gatherSlots);
         } else {
             CUDA_TRY(cudaFuncSetAttribute(ewb::rowGatherHalfKernel<20, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ewb::rowGatherHalfKernel<20, W><<<grid, W * 32, smem, st>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, V, b->csr_data, p->maxDeg);
+            ewb::rowGatherHalfKernel<20, W><<<grid, W * 32, smem, st>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, V, b->csr_data, p->maxDeg, p->gatherOrder, p->gatherSlots);
         }
         LAUNCH_CHECK();
         return EWB_OK;

@@ -294,6 +294,30 @@ __global__ void __launch_bounds__(WARPS * 32) rowGatherKernel(int64_t nNode, con
     for (int i = lane; i < 3 * rowLen; i += 32) out[i] = buf[i];
 }
 
+// Precomputed element-to-CSR-slot map of the row gather: for incidence k = (node A, element e, local node a) and every local
+// node b of e, the position of conn[e][b] in A's sorted neighbour list (node degree <= 255: one byte).  Built once per plan.
+template <int NN>
+__global__ void gatherSlotKernel(int64_t nNode, const int64_t* __restrict__ adjPtr, const int32_t* __restrict__ adj,
+                                 const int64_t* __restrict__ incPtr, const int32_t* __restrict__ inc, const int32_t* __restrict__ conn,
+                                 unsigned char* __restrict__ slotTab) {
+    const int64_t A = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (A >= nNode || lane >= NN) return;
+    const int64_t s0 = adjPtr[A];
+    const int deg = (int)(adjPtr[A + 1] - s0);
+    const int32_t* nb = adj + s0;
+    for (int64_t k = incPtr[A]; k < incPtr[A + 1]; ++k) {
+        const int64_t e = inc[k] / NN;
+        const int32_t B = conn[e * NN + lane];
+        int lo = 0, hi = deg - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (nb[mid] < B) lo = mid + 1; else hi = mid;
+        }
+        slotTab[k * NN + lane] = (unsigned char)lo;
+    }
+}
+
 // CSRGenerator.updateCSR on the half-block scratch (HalfLayout): one warp per node A, lane b < NN owns the block (a, b) of the
 // incident element (e, a) — stored as K[a][a+d] if d = b - a (mod NN) < nb(a), else as the transpose of K[b][b+d'] — and adds it
 // to A's three CSR rows in shared memory.  Elements are visited in ascending order (== ascending COO index, the reference's
@@ -302,13 +326,15 @@ template <int NN, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) rowGatherHalfKernel(int64_t nNode, const int64_t* __restrict__ adjPtr, const int32_t* __restrict__ adj,
                                                                   const int64_t* __restrict__ incPtr, const int32_t* __restrict__ inc,
                                                                   const int32_t* __restrict__ conn, const double* __restrict__ S, double* __restrict__ data,
-                                                                  int maxDeg) {
+                                                                  int maxDeg, const int32_t* __restrict__ order,
+                                                                  const unsigned char* __restrict__ slotTab) {
     using HL = HalfLayout<NN>;
     static_assert(NN <= 32, "one lane per element node");
     extern __shared__ double rowBufAll[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t A = (int64_t)blockIdx.x * WARPS + warp;
-    if (A >= nNode) return;
+    const int64_t slotA = (int64_t)blockIdx.x * WARPS + warp;
+    if (slotA >= nNode) return;
+    const int64_t A = order ? order[slotA] : slotA;  // visiting order only (locality of the scratch reads)
     double* buf = rowBufAll + (size_t)warp * 9 * maxDeg;
     const int64_t s0 = adjPtr[A];
     const int deg = (int)(adjPtr[A + 1] - s0);
@@ -328,13 +354,17 @@ __global__ void __launch_bounds__(WARPS * 32) rowGatherHalfKernel(int64_t nNode,
         const double* src = S + e * (int64_t)HL::SE + (direct ? a * HL::SA + d * 9 : b * HL::SA + (NN - d) * 9);
 #pragma unroll
         for (int i = 0; i < 9; ++i) v[i] = src[i];
-        const int32_t B = conn[e * NN + b];
-        int lo = 0, hi = deg - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (nb[mid] < B) lo = mid + 1; else hi = mid;
+        if (slotTab) {
+            slot = slotTab[k * NN + b];
+        } else {
+            const int32_t B = conn[e * NN + b];
+            int lo = 0, hi = deg - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (nb[mid] < B) lo = mid + 1; else hi = mid;
+            }
+            slot = lo;
         }
-        slot = lo;
     };
     double v[9], w[9];
     int slot = 0, slotN = 0;

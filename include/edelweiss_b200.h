@@ -105,6 +105,11 @@ int ewb_plan_slot_map(const ewb_plan* plan, int64_t e0, int64_t e1, int32_t* x_d
  * The connectivity is verified against the generator's closed form; enables the fused sweep kernel. */
 int ewb_plan_set_box(ewb_plan* plan, int64_t nX, int64_t nY, int64_t nZ);
 int ewb_plan_is_box(const ewb_plan* plan);
+/* Optional locality hint for the arbitrary-mesh path: the order (a permutation of 0..n_node-1, host array) in which the row
+ * gather visits the nodes.  Every block of the element scratch is read by two nodes; visiting spatially close nodes together
+ * (the host layer passes a Morton order of the coordinates) lets the second read hit L2.  Results do not depend on it.
+ * NULL restores the node order.  No counterpart in the reference (csrgenerator.pyx:100-115 is a serial scatter). */
+int ewb_plan_set_gather_order(ewb_plan* plan, const int32_t* order_host);
 
 /* ---- the hot path ---------------------------------------------------------------------------
  * One NIST.computeElements pass + CSRGenerator.updateCSR on the device
