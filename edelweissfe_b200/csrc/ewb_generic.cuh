@@ -11,13 +11,14 @@ namespace ewb {
 
 // Internal scratch of the arbitrary-mesh path ("half-block" layout): only the blocks the element loop computes are stored,
 // K[a][a + d] for d = 0 .. NN/2 (node pairs in circulant order, Ke is symmetric), 9 doubles each, contiguous per node a:
-//   S[e][a][d][3][3]  at  e * SE + a * SA + 9 d,   SA = 9 (NN/2 + 1) rounded up to even (16-byte aligned runs).
-// 55 % of the VIJ bytes (reference layout: 9 NN^2 doubles per element), written as 16-byte stores of runs that are contiguous
+//   S[e][a][d][3][3]  at  e * SE + a * SA + 10 d   (9 values + 1 pad: 16-byte aligned blocks),   SA = 10 (NN/2 + 1).
+// 61 % of the VIJ bytes (reference layout: 9 NN^2 doubles per element), written as 16-byte stores of runs that are contiguous
 // per thread; rowGatherHalfKernel reads block (a, b) either directly (d = b - a < nb(a)) or as the transpose of (b, a).
 template <int NN>
 struct HalfLayout {
     static constexpr int HALF = NN / 2, NB = HALF + 1;
-    static constexpr int SA = (NB * 9 + 1) & ~1;
+    static constexpr int BS = 10;  // block stride: 9 values + 1 pad, so that every block is 16-byte aligned (5 x 128-bit accesses)
+    static constexpr int SA = NB * BS;
     static constexpr int SE = NN * SA;
 };
 
@@ -34,15 +35,15 @@ struct HalfEmit {
     template <int BLK>
     __device__ __forceinline__ void pass(int a, int ps, const double (&out)[BLK * 9 + 1]) const {
         using HL = HalfLayout<NN>;
-        constexpr int NPASS = (HL::NB + BLK - 1) / BLK;
-        static_assert(NPASS == 1 || (BLK * 9) % 2 == 0, "runs of later passes must stay 16-byte aligned");
-        double2* dst = reinterpret_cast<double2*>(S + a * HL::SA + ps * (BLK * 9));
-        // doubles of this pass: blocks d = ps*BLK .. min(NB, (ps+1)*BLK) - 1, rounded up to a pair (the pad slot exists in SA)
-        const int nBlk = min(BLK, HL::NB - ps * BLK);
-        const int nPair = (nBlk * 9 + 1) >> 1;
+        double2* dst = reinterpret_cast<double2*>(S + a * HL::SA + ps * (BLK * HL::BS));
+        const int nBlk = min(BLK, HL::NB - ps * BLK);  // blocks d = ps*BLK .. ps*BLK + nBlk - 1
 #pragma unroll
-        for (int q = 0; q < (BLK * 9 + 1) / 2; ++q)
-            if (q < nPair) dst[q] = make_double2(out[2 * q], out[2 * q + 1]);
+        for (int k = 0; k < BLK; ++k)
+            if (k < nBlk) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dst[k * 5 + q] = make_double2(out[k * 9 + 2 * q], out[k * 9 + 2 * q + 1]);
+                dst[k * 5 + 4] = make_double2(out[k * 9 + 8], 0.0);
+            }
     }
 };
 
@@ -133,11 +134,15 @@ __device__ __forceinline__ void phaseBDmma20LE(const double* sm, int lane, const
                         for (int j = 0; j < 3; ++j) K[i * 3 + j] = mp.lambda * c[i][j][t] + mp.G * c[j][i][t] + (i == j ? tr : 0.0);
                     const int d = b - a;
                     const bool direct = d < HL::HALF + (a < HL::HALF ? 1 : 0);
-                    double* dst = Se + (direct ? a * HL::SA + d * 9 : b * HL::SA + (NN - d) * 9);
+                    double2* dst = reinterpret_cast<double2*>(Se + (direct ? a * HL::SA + d * HL::BS : b * HL::SA + (NN - d) * HL::BS));
+                    double o[10];
 #pragma unroll
                     for (int i = 0; i < 3; ++i)
 #pragma unroll
-                        for (int j = 0; j < 3; ++j) dst[i * 3 + j] = direct ? K[i * 3 + j] : K[j * 3 + i];
+                        for (int j = 0; j < 3; ++j) o[i * 3 + j] = direct ? K[i * 3 + j] : K[j * 3 + i];
+                    o[9] = 0.0;
+#pragma unroll
+                    for (int qq = 0; qq < 5; ++qq) dst[qq] = make_double2(o[2 * qq], o[2 * qq + 1]);
                 }
             }
         }
@@ -323,7 +328,7 @@ __global__ void gatherSlotKernel(int64_t nNode, const int64_t* __restrict__ adjP
 // to A's three CSR rows in shared memory.  Elements are visited in ascending order (== ascending COO index, the reference's
 // summation order); the next element's block travels while the current one is added.
 template <int NN, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) rowGatherHalfKernel(int64_t nNode, const int64_t* __restrict__ adjPtr, const int32_t* __restrict__ adj,
+__global__ void __launch_bounds__(WARPS * 32, 4) rowGatherHalfKernel(int64_t nNode, const int64_t* __restrict__ adjPtr, const int32_t* __restrict__ adj,
                                                                   const int64_t* __restrict__ incPtr, const int32_t* __restrict__ inc,
                                                                   const int32_t* __restrict__ conn, const double* __restrict__ S, double* __restrict__ data,
                                                                   int maxDeg, const int32_t* __restrict__ order,
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowGatherHalfKernel(int64_t nNode,
     const int32_t* nb = adj + s0;
     const int64_t k0 = incPtr[A], k1 = incPtr[A + 1];
     // fetch: this lane's block of incident element k (registers) and its slot in A's sorted neighbour list
-    auto fetch = [&](int64_t k, double (&v)[9], int& slot, bool& direct) {
+    auto fetch = [&](int64_t k, double2 (&v)[5], int& slot, bool& direct) {
         const int32_t ea = inc[k];
         const int64_t e = ea / NN;
         const int a = ea % NN;
@@ -351,9 +356,9 @@ __global__ void __launch_bounds__(WARPS * 32) rowGatherHalfKernel(int64_t nNode,
         int d = b - a;
         if (d < 0) d += NN;
         direct = d < HL::HALF + (a < HL::HALF ? 1 : 0);
-        const double* src = S + e * (int64_t)HL::SE + (direct ? a * HL::SA + d * 9 : b * HL::SA + (NN - d) * 9);
+        const double2* src = reinterpret_cast<const double2*>(S + e * (int64_t)HL::SE + (direct ? a * HL::SA + d * HL::BS : b * HL::SA + (NN - d) * HL::BS));
 #pragma unroll
-        for (int i = 0; i < 9; ++i) v[i] = src[i];
+        for (int i = 0; i < 5; ++i) v[i] = src[i];
         if (slotTab) {
             slot = slotTab[k * NN + b];
         } else {
@@ -366,7 +371,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowGatherHalfKernel(int64_t nNode,
             slot = lo;
         }
     };
-    double v[9], w[9];
+    double2 v[5], w[5];
     int slot = 0, slotN = 0;
     bool direct = true, directN = true;
     if (lane < NN && k0 < k1) fetch(k0, v, slot, direct);
@@ -375,12 +380,13 @@ __global__ void __launch_bounds__(WARPS * 32) rowGatherHalfKernel(int64_t nNode,
         if (lane < NN) {
             if (k + 1 < k1) fetch(k + 1, w, slotN, directN);
             double* dst = buf + 3 * slot;
+            const double x[9] = {v[0].x, v[0].y, v[1].x, v[1].y, v[2].x, v[2].y, v[3].x, v[3].y, v[4].x};
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
-                for (int j = 0; j < 3; ++j) dst[i * rowLen + j] += direct ? v[i * 3 + j] : v[j * 3 + i];
+                for (int j = 0; j < 3; ++j) dst[i * rowLen + j] += direct ? x[i * 3 + j] : x[j * 3 + i];
 #pragma unroll
-            for (int i = 0; i < 9; ++i) v[i] = w[i];
+            for (int i = 0; i < 5; ++i) v[i] = w[i];
             slot = slotN;
             direct = directN;
         }
