@@ -34,7 +34,10 @@ __device__ __forceinline__ void forNodes(Fn&& f) {
 template <int NN, int NGP, int MC>
 struct TileLayout {
     static constexpr bool HASQ = (MC != MC_LE);
-    static constexpr int GST = NN * 3 + 1;  // Gauss-point stride of the vector tables (odd: conflict-light)
+    // Gauss-point stride of the vector tables.  8 nodes: odd (conflict-free phase-A stores, lane = Gauss point).  20 nodes: 60, which
+    // makes the mma fragment loads of phaseBDmma20LE (lane = node row x Gauss point: 60 q + 3 r) conflict-free; they outnumber the
+    // stores 4 : 1 (61 gave 4-way conflicts on the loads: 2x the ideal wavefront count in the ncu source view).
+    static constexpr int GST = NN == 20 ? 60 : NN * 3 + 1;
     // per-Gauss-point scalars: [0..3] tangent coefficients (already * w detJ), [4..9] -w detJ * stress
     // (tensor order xx,yy,zz,xy,xz,yz), [10..18] F (only W_b needs it in phase B)
     // hypo-elastic TL: [10..18] F, [20..25] w detJ mu' (F F^T) (xx,yy,zz,xy,xz,yz); Q holds f_a = F grad N_a, R holds p_a = F N grad N_a
