@@ -160,6 +160,56 @@ def test_cutback_flag():
         asm.poll()
 
 
+def test_inverted_element_is_reported():
+    """The linear-elastic sweep publishes sqrt(w detJ) grad N: an element with a non-positive Jacobian determinant must surface
+    as an error from poll() (status bit 3), not as NaNs in the matrix; the arbitrary-mesh path still handles the mesh."""
+    import torch
+
+    from edelweissfe_b200 import ElementAssembly, box_mesh
+    from edelweissfe_b200._lib import EwbError
+
+    n = (6, 6, 6)
+    coords, conn = box_mesh(*n, lX=6.0, lY=6.0, lZ=6.0)
+    coords = coords.copy()
+    mid = ((3 * 7) + 3) * 7 + 3  # interior node pushed far through its neighbours: the adjacent elements invert
+    coords[mid, 0] += 2.5
+    asm = ElementAssembly("C3D8", conn, coords, "linearelastic", [2.1e4, 0.22], box=n)
+    asm.assemble()
+    with pytest.raises(EwbError, match="Jacobian"):
+        asm.poll()
+    asm.assemble(flags=2)  # EWB_FLAG_FORCE_GENERIC
+    asm.poll()
+    assert torch.isfinite(asm.csr_data).all()
+
+
+def test_gather_order_hint_does_not_change_results():
+    """ewb_plan_set_gather_order only changes the visiting order of the row gather."""
+    import ctypes as C
+
+    from edelweissfe_b200 import ElementAssembly, box_mesh
+    from edelweissfe_b200.assembly import morton_order
+
+    coords, conn = box_mesh(5, 4, 3, lX=5.0, lY=4.0, lZ=3.0, elType="C3D20")
+    rng = np.random.default_rng(1)
+    dU = 1e-3 * rng.standard_normal(3 * coords.shape[0])
+    out = []
+    for hint in (False, True):
+        asm = ElementAssembly("C3D20", conn, coords, "linearelastic", [2.1e4, 0.22])
+        if hint:
+            order = morton_order(coords)
+            assert sorted(order.tolist()) == list(range(coords.shape[0]))
+            assert asm.lib.ewb_plan_set_gather_order(asm.plan, order.ctypes.data_as(C.c_void_p)) == 0
+            bad = order.copy()
+            bad[0] = bad[1]
+            assert asm.lib.ewb_plan_set_gather_order(asm.plan, bad.ctypes.data_as(C.c_void_p)) < 0  # not a permutation
+            assert asm.lib.ewb_plan_set_gather_order(asm.plan, order.ctypes.data_as(C.c_void_p)) == 0
+        asm.dU.copy_(__import__("torch").as_tensor(dU))
+        asm.assemble()
+        asm.poll()
+        out.append(asm.csr_data.cpu().numpy().copy())
+    assert np.array_equal(out[0], out[1])
+
+
 def test_compute_host_matches_oracle():
     """The host-facing call the NISTB200 plugin uses (pinned host buffers, AoS state in/out)."""
     from edelweissfe_b200 import ElementAssembly, box_mesh
