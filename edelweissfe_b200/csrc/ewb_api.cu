@@ -114,37 +114,37 @@ int materialClass(int elType, int material, const double* props, int nProps, ewb
 }
 
 template <int NN, int NGP, int MC, bool TL, int T, int E, int BLK>
-int launchVij(ewb_plan* p, const ewb::MatParams& mp, const ewb_buffers* b, double* V, double* Pe, cudaStream_t st, int transposed) {
+int launchVij(ewb_plan* p, const ewb::MatParams& mp, const ewb_buffers* b, double* V, double* Pe, cudaStream_t st, int halfScratch) {
     using L = ewb::TileLayout<NN, NGP, MC>;
     auto kern = ewb::computeElementsVijKernel<NN, NGP, MC, TL, T, E, BLK>;
     const size_t smem = (size_t)E * L::PER_EL * sizeof(double);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = (p->nEl + E - 1) / E;
-    kern<<<(unsigned)grid, T * E, smem, st>>>(p->nEl, p->conn, b->coords, b->U, b->dU, b->state_ref, b->state_temp, V, Pe, mp, p->failFlag, transposed);
+    kern<<<(unsigned)grid, T * E, smem, st>>>(p->nEl, p->conn, b->coords, b->U, b->dU, b->state_ref, b->state_temp, V, Pe, mp, p->failFlag, halfScratch);
     LAUNCH_CHECK();
     return EWB_OK;
 }
 
-int dispatchVij(ewb_plan* p, int mc, const ewb::MatParams& mp, const ewb_buffers* b, double* V, double* Pe, cudaStream_t st, int transposed = 0) {
+int dispatchVij(ewb_plan* p, int mc, const ewb::MatParams& mp, const ewb_buffers* b, double* V, double* Pe, cudaStream_t st, int halfScratch = 0) {
     if (p->elType == EWB_C3D8) {
-        if (mc == ewb::MC_LE) return launchVij<8, 8, ewb::MC_LE, false, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
-        if (mc == ewb::MC_VM) return launchVij<8, 8, ewb::MC_VM, false, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_LE) return launchVij<8, 8, ewb::MC_LE, false, 8, 16, 5>(p, mp, b, V, Pe, st, halfScratch);
+        if (mc == ewb::MC_VM) return launchVij<8, 8, ewb::MC_VM, false, 8, 16, 5>(p, mp, b, V, Pe, st, halfScratch);
     } else if (p->elType == EWB_C3D8TL) {
-        if (mc == ewb::MC_NH) return launchVij<8, 8, ewb::MC_NH, true, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
-        if (mc == ewb::MC_TLE) return launchVij<8, 8, ewb::MC_TLE, true, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);  // element.py:415-425
-        if (mc == ewb::MC_TLV) return launchVij<8, 8, ewb::MC_TLV, true, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_NH) return launchVij<8, 8, ewb::MC_NH, true, 8, 16, 5>(p, mp, b, V, Pe, st, halfScratch);
+        if (mc == ewb::MC_TLE) return launchVij<8, 8, ewb::MC_TLE, true, 8, 16, 5>(p, mp, b, V, Pe, st, halfScratch);  // element.py:415-425
+        if (mc == ewb::MC_TLV) return launchVij<8, 8, ewb::MC_TLV, true, 8, 16, 5>(p, mp, b, V, Pe, st, halfScratch);
     } else if (p->elType == EWB_C3D20) {
-        if (mc == ewb::MC_LE) return launchVij<20, 27, ewb::MC_LE, false, 32, 4, 4>(p, mp, b, V, Pe, st, transposed);
-        if (mc == ewb::MC_VM) return launchVij<20, 27, ewb::MC_VM, false, 32, 4, 4>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_LE) return launchVij<20, 27, ewb::MC_LE, false, 32, 4, 4>(p, mp, b, V, Pe, st, halfScratch);
+        if (mc == ewb::MC_VM) return launchVij<20, 27, ewb::MC_VM, false, 32, 4, 4>(p, mp, b, V, Pe, st, halfScratch);
     } else if (p->elType == EWB_C3D8R) {
-        if (mc == ewb::MC_LE) return launchVij<8, 1, ewb::MC_LE, false, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
-        if (mc == ewb::MC_VM) return launchVij<8, 1, ewb::MC_VM, false, 8, 16, 5>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_LE) return launchVij<8, 1, ewb::MC_LE, false, 8, 16, 5>(p, mp, b, V, Pe, st, halfScratch);
+        if (mc == ewb::MC_VM) return launchVij<8, 1, ewb::MC_VM, false, 8, 16, 5>(p, mp, b, V, Pe, st, halfScratch);
     } else if (p->elType == EWB_C3D8E) {
-        if (mc == ewb::MC_LE) return launchVij<8, 27, ewb::MC_LE, false, 32, 4, 5>(p, mp, b, V, Pe, st, transposed);
-        if (mc == ewb::MC_VM) return launchVij<8, 27, ewb::MC_VM, false, 32, 4, 5>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_LE) return launchVij<8, 27, ewb::MC_LE, false, 32, 4, 5>(p, mp, b, V, Pe, st, halfScratch);
+        if (mc == ewb::MC_VM) return launchVij<8, 27, ewb::MC_VM, false, 32, 4, 5>(p, mp, b, V, Pe, st, halfScratch);
     } else if (p->elType == EWB_C3D20R) {
-        if (mc == ewb::MC_LE) return launchVij<20, 8, ewb::MC_LE, false, 32, 4, 4>(p, mp, b, V, Pe, st, transposed);
-        if (mc == ewb::MC_VM) return launchVij<20, 8, ewb::MC_VM, false, 32, 4, 4>(p, mp, b, V, Pe, st, transposed);
+        if (mc == ewb::MC_LE) return launchVij<20, 8, ewb::MC_LE, false, 32, 4, 4>(p, mp, b, V, Pe, st, halfScratch);
+        if (mc == ewb::MC_VM) return launchVij<20, 8, ewb::MC_VM, false, 32, 4, 4>(p, mp, b, V, Pe, st, halfScratch);
     }
     return fail(EWB_ERR_UNSUPPORTED, "element/material combination not implemented");
 }
@@ -454,8 +454,8 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
             V = p->vijScratch;
         }
     }
-    const bool internalV = wantK && V == p->vijScratch;  // nobody else reads it: use the gather-friendly transposed layout
-    if (int rc = dispatchVij(p, mc, mp, b, V, p->peScratch, st, internalV ? 2 : 0)) return rc;
+    const bool internalV = wantK && V == p->vijScratch;  // nobody else reads it: half-block scratch (HalfLayout)
+    if (int rc = dispatchVij(p, mc, mp, b, V, p->peScratch, st, internalV ? 1 : 0)) return rc;
     {
         const int B = 256;
         const unsigned grid = (unsigned)((3 * p->nNode + B - 1) / B);

@@ -190,8 +190,9 @@ __device__ __forceinline__ void vonMises(const MatParams& mp, const double de[6]
         double dk = 0.0;
         int counter = 0;
         const double G = mp.G;
+        double ex;
         while (true) {
-            const double ex = exp(-mp.delta * (k0 + dk));
+            ex = exp(-mp.delta * (k0 + dk));
             const double R = devn - s6 * G * dk - s23 * (mp.fy0 + mp.HLin * (k0 + dk) + mp.dfy * (1.0 - ex));
             if (!(fabs(R) > 1e-12)) break;
             if (counter == 15) {
@@ -210,7 +211,7 @@ __device__ __forceinline__ void vonMises(const MatParams& mp, const double de[6]
             r.n[i] = d[i] * inv;
             s[i] = t[i] - 2.0 * G * dLambda * r.n[i];
         }
-        const double dfyk = mp.HLin + mp.dfy * mp.delta * exp(-mp.delta * kappa);
+        const double dfyk = mp.HLin + mp.dfy * mp.delta * ex;  // ex == exp(-delta * kappa): the loop's last evaluation
         const double bcoef = 4.0 * G * G * dLambda * inv;
         r.a = 2.0 * G * (1.0 / (1.0 + dfyk / (3.0 * G)) - 2.0 * G * dLambda * inv);
         r.lam = mp.lambda + bcoef * third;

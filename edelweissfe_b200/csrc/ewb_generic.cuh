@@ -53,22 +53,19 @@ struct VijEmit {
     template <int BLK>
     __device__ __forceinline__ void pass(int, int, const double (&)[BLK * 9 + 1]) const {}
     static constexpr int ND = 3 * NN;
-    double* V;   // element slice [ND*ND] or nullptr
+    double* V;   // element slice [ND*ND] in the reference's VIJ layout, Ke row-major (element.py:318), or nullptr
     double* Pe;  // element slice [ND]
-    // false: the reference's VIJ layout, Ke row-major (element.py:318).  true: internal scratch, Ke^T row-major, so that the rows
-    // of one node (global K gets Ke^T, dofmanager.py:552-553) are 3 contiguous runs of ND doubles for rowGatherKernel.
-    bool transposed;
     __device__ __forceinline__ void residual(int a, const double P[3]) const {
 #pragma unroll
         for (int i = 0; i < 3; ++i) Pe[3 * a + i] = P[i];
     }
     __device__ __forceinline__ void block(int a, int b, const double K[9]) const {
         if (V == nullptr) return;
-        double* d = transposed ? V + (3 * b) * ND + 3 * a : V + (3 * a) * ND + 3 * b;
+        double* d = V + (3 * a) * ND + 3 * b;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) d[transposed ? j * ND + i : i * ND + j] = K[i * 3 + j];
+            for (int j = 0; j < 3; ++j) d[i * ND + j] = K[i * 3 + j];
     }
 };
 
@@ -155,7 +152,7 @@ __global__ void __launch_bounds__(T* E, (NN == 20 ? 3 : 1)) computeElementsVijKe
                                                                 const double* __restrict__ U, const double* __restrict__ dU,
                                                                 const double* __restrict__ stateRef, double* __restrict__ stateTemp,
                                                                 double* __restrict__ V, double* __restrict__ Pe, MatParams mp, int* failFlag,
-                                                                int transposed) {
+                                                                int halfScratch) {  // halfScratch: V is the internal half-block scratch (HalfLayout), else the reference's VIJ array
     using L = TileLayout<NN, NGP, MC>;
     extern __shared__ double smem[];
     const int el = threadIdx.x / T, t = threadIdx.x % T;
@@ -178,7 +175,7 @@ __global__ void __launch_bounds__(T* E, (NN == 20 ? 3 : 1)) computeElementsVijKe
     // phase B work items: (node row a, pass of BLK circulant blocks), spread over the T threads of the element
     constexpr int NPASS = (NN / 2 + 1 + BLK - 1) / BLK;
     if constexpr (NN == 20 && MC == MC_LE && T == 32) {
-        if (active && transposed == 2 && V != nullptr) {  // warp-uniform: one warp per element
+        if (active && halfScratch && V != nullptr) {  // warp-uniform: one warp per element
             if (t < NN) {
                 HalfEmit<NN> emit{V + e * (int64_t)HalfLayout<NN>::SE, Pe + e * (3 * NN)};
                 nodeRow<NN, NGP, MC, BLK>(sm, t, mp, false, emit);  // residual row only
@@ -192,11 +189,11 @@ __global__ void __launch_bounds__(T* E, (NN == 20 ? 3 : 1)) computeElementsVijKe
 #pragma unroll 1
         for (int it = t; it < NN * NPASS; it += T) {
             const int a = it % NN, ps = it / NN;
-            if (transposed == 2) {  // internal half-block scratch
+            if (halfScratch) {  // internal half-block scratch
                 HalfEmit<NN> emit{V + e * (int64_t)HalfLayout<NN>::SE, Pe + e * (3 * NN)};
                 nodeRow<NN, NGP, MC, BLK>(sm, a, mp, V != nullptr, emit, ps, ps + 1, ps == 0);
             } else {
-                VijEmit<NN> emit{V ? V + e * (int64_t)(9 * NN * NN) : nullptr, Pe + e * (3 * NN), transposed != 0};
+                VijEmit<NN> emit{V ? V + e * (int64_t)(9 * NN * NN) : nullptr, Pe + e * (3 * NN)};
                 nodeRow<NN, NGP, MC, BLK>(sm, a, mp, V != nullptr, emit, ps, ps + 1, ps == 0);
             }
         }
@@ -244,59 +241,6 @@ __global__ void updateCsrKernel(int64_t nNode, const int64_t* __restrict__ adjPt
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) data[base + i * 3 * deg + 3 * s + j] = acc[i * 3 + j];
-}
-
-// CSRGenerator.updateCSR on the TRANSPOSED internal scratch: one warp per node A accumulates its three CSR rows in shared
-// memory, element by element in ascending element order (== ascending COO index, the same summation order as
-// updateCsrKernel), reading 3 runs of ND contiguous doubles per incident element, and writes the rows once, coalesced.
-// rowBuf: 9 * maxDeg doubles per warp.
-template <int NN, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) rowGatherKernel(int64_t nNode, const int64_t* __restrict__ adjPtr, const int32_t* __restrict__ adj,
-                                                              const int64_t* __restrict__ incPtr, const int32_t* __restrict__ inc,
-                                                              const int32_t* __restrict__ conn, const double* __restrict__ Vt, double* __restrict__ data,
-                                                              int maxDeg) {
-    constexpr int ND = 3 * NN;
-    static_assert(NN <= 32, "one lane per element node");
-    extern __shared__ double rowBufAll[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t A = (int64_t)blockIdx.x * WARPS + warp;
-    if (A >= nNode) return;
-    double* buf = rowBufAll + (size_t)warp * 9 * maxDeg;
-    const int64_t s0 = adjPtr[A];
-    const int deg = (int)(adjPtr[A + 1] - s0);
-    const int rowLen = 3 * deg;
-    for (int i = lane; i < 3 * rowLen; i += 32) buf[i] = 0.0;
-    __syncwarp();
-    const int32_t* nb = adj + s0;
-    for (int64_t k = incPtr[A]; k < incPtr[A + 1]; ++k) {
-        const int32_t ea = inc[k];
-        const int64_t e = ea / NN;
-        const int a = ea % NN;
-        // slot of every node of the element inside A's sorted neighbour list (binary search, lane b < NN)
-        int slot = 0;
-        if (lane < NN) {
-            const int32_t B = conn[e * NN + lane];
-            int lo = 0, hi = deg - 1;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (nb[mid] < B) lo = mid + 1; else hi = mid;
-            }
-            slot = lo;
-        }
-        const double* rows = Vt + e * (int64_t)(ND * ND) + (int64_t)(3 * a) * ND;
-#pragma unroll
-        for (int it = 0; it < (3 * ND + 31) / 32; ++it) {  // uniform trip count: every lane takes part in the shuffle
-            const int idx = it * 32 + lane;
-            const bool ok = idx < 3 * ND;
-            const int i = ok ? idx / ND : 0, c = ok ? idx - i * ND : 0;
-            const int b = c / 3, j = c - 3 * b;
-            const int s = __shfl_sync(0xffffffffu, slot, b);
-            if (ok) buf[i * rowLen + 3 * s + j] += rows[idx];
-        }
-        __syncwarp();
-    }
-    double* out = data + 9 * s0;
-    for (int i = lane; i < 3 * rowLen; i += 32) out[i] = buf[i];
 }
 
 // Precomputed element-to-CSR-slot map of the row gather: for incidence k = (node A, element e, local node a) and every local
