@@ -2,8 +2,9 @@
 // data flow:   NIST.computeElements  -> VIJ values + per-element Pe     (nonlinearimplicitstatic.py:794-849)
 //              CSRGenerator.updateCSR -> CSR data, summed in ascending COO order (csrgenerator.pyx:100-115)
 //              P[el] += Pe ; F[el] += |Pe| -> gathered per node in ascending element order (:843-844)
-// Deterministic (no atomics).  It materialises V like the reference does, so it moves ~3.5x the
-// algorithmic bytes; the fused BoxGen sweep (ewb_sweep.cuh) is the fast path.
+// Deterministic (no atomics).  The intermediate is either the reference's V array (ewb_compute_elements_vij / ewb_update_csr,
+// bit-for-bit the reference's data flow) or, inside ewb_assemble, the half-block scratch below; either way the path moves
+// 2-3x the algorithmic bytes, so the fused BoxGen sweep (ewb_sweep.cuh) is the fast path for structured meshes.
 #pragma once
 #include "ewb_tile.cuh"
 

@@ -127,3 +127,22 @@ def test_slab_ranges():
     lay = SlabLayout(10, 3, 2, 1, 3)
     assert (lay.a, lay.b, lay.nXloc) == (4, 7, 3)
     assert lay.ownedDofs == lay.nDofLoc - lay.planeDofs and lay.node_offset() == 4 * 12
+
+
+def test_morton_order_is_a_locality_preserving_permutation():
+    """Host helper behind ewb_plan_set_gather_order: a permutation, and consecutive nodes stay spatially close."""
+    import numpy as np
+
+    from edelweissfe_b200 import box_mesh
+    from edelweissfe_b200.assembly import morton_order
+
+    coords, _ = box_mesh(7, 6, 5, lX=7.0, lY=6.0, lZ=5.0, elType="C3D20")
+    order = morton_order(coords)
+    assert order.dtype == np.int32 and sorted(order.tolist()) == list(range(coords.shape[0]))
+    step = np.linalg.norm(np.diff(coords[order], axis=0), axis=1)
+    natural = np.linalg.norm(np.diff(coords, axis=0), axis=1)
+    assert np.median(step) <= np.median(natural) * 1.5 and step.mean() < 0.5 * np.linalg.norm(coords.max(0) - coords.min(0))
+    # degenerate input (all nodes in a plane) must not divide by zero
+    flat = coords.copy()
+    flat[:, 2] = 1.0
+    assert sorted(morton_order(flat).tolist()) == list(range(coords.shape[0]))
