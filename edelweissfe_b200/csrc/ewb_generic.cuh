@@ -292,12 +292,15 @@ __global__ void __launch_bounds__(WARPS * 32, 4) rowGatherHalfKernel(int64_t nNo
     for (int i = lane; i < 3 * rowLen; i += 32) buf[i] = 0.0;
     const int32_t* nb = adj + s0;
     const int64_t k0 = incPtr[A], k1 = incPtr[A + 1];
+    constexpr int G = NN <= 8 ? 32 / NN : 1;  // incident elements per batch
+    const int g = lane / NN, lb = lane - g * NN;
+    const bool laneOn = lane < G * NN;
     // fetch: this lane's block of incident element k (registers) and its slot in A's sorted neighbour list
     auto fetch = [&](int64_t k, double2 (&v)[5], int& slot, bool& direct) {
         const int32_t ea = inc[k];
         const int64_t e = ea / NN;
         const int a = ea % NN;
-        const int b = lane;
+        const int b = lb;
         int d = b - a;
         if (d < 0) d += NN;
         direct = d < HL::HALF + (a < HL::HALF ? 1 : 0);
@@ -319,23 +322,31 @@ __global__ void __launch_bounds__(WARPS * 32, 4) rowGatherHalfKernel(int64_t nNo
     double2 v[5], w[5];
     int slot = 0, slotN = 0;
     bool direct = true, directN = true;
-    if (lane < NN && k0 < k1) fetch(k0, v, slot, direct);
+    // 8-node elements: four incident elements per batch (lane group g = lane / NN takes element kb + g), so that all 32 lanes
+    // fetch; the groups then add one after the other (ascending element order, and two elements may hit the same CSR entry).
+    bool have = laneOn && k0 + g < k1;
+    if (have) fetch(k0 + g, v, slot, direct);
     __syncwarp();
-    for (int64_t k = k0; k < k1; ++k) {
-        if (lane < NN) {
-            if (k + 1 < k1) fetch(k + 1, w, slotN, directN);
-            double* dst = buf + 3 * slot;
-            const double x[9] = {v[0].x, v[0].y, v[1].x, v[1].y, v[2].x, v[2].y, v[3].x, v[3].y, v[4].x};
+    for (int64_t kb = k0; kb < k1; kb += G) {
+        const bool haveN = laneOn && kb + G + g < k1;
+        if (haveN) fetch(kb + G + g, w, slotN, directN);
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+        for (int gg = 0; gg < G; ++gg) {
+            if (have && g == gg) {
+                double* dst = buf + 3 * slot;
+                const double x[9] = {v[0].x, v[0].y, v[1].x, v[1].y, v[2].x, v[2].y, v[3].x, v[3].y, v[4].x};
 #pragma unroll
-                for (int j = 0; j < 3; ++j) dst[i * rowLen + j] += direct ? x[i * 3 + j] : x[j * 3 + i];
+                for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int i = 0; i < 5; ++i) v[i] = w[i];
-            slot = slotN;
-            direct = directN;
+                    for (int j = 0; j < 3; ++j) dst[i * rowLen + j] += direct ? x[i * 3 + j] : x[j * 3 + i];
+            }
+            __syncwarp();
         }
-        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 5; ++i) v[i] = w[i];
+        slot = slotN;
+        direct = directN;
+        have = haveN;
     }
     double* out = data + 9 * s0;
     for (int i = lane; i < 3 * rowLen; i += 32) out[i] = buf[i];
