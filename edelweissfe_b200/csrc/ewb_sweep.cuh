@@ -886,7 +886,7 @@ __global__ void __launch_bounds__(((TY + 1) / 2) * ((TZ + 1) / 2) * 32, 1) sweep
         const int pfBase = (aHi ? pfHi : pfLo) + (ndy(na) * TZ + ndz(na)) * 6;
         const bool planeOwned = aHi ? hiOwned : loOwned;
         // ------------- phase B: 4 colour rounds, one element per round -------------
-#pragma unroll 1
+#pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int Rnd = 4 * step + k;
             const bool valid = (validMask >> k) & 1;
