@@ -3,6 +3,7 @@
 // CSRGenerator.__init__ of the reference) and kernel dispatch.  No torch types, no CPU fallback:
 // every compute entry point launches CUDA kernels or fails.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -12,12 +13,13 @@
 #include "../../include/edelweiss_b200.h"
 #include "ewb_generic.cuh"
 #include "ewb_sweep.cuh"
-#include "ewb_staged.cuh"
+#include "ewb_rowpipe.cuh"
 
 namespace {
 
 thread_local std::string g_err;
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
+inline void countLaunch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -32,7 +34,7 @@ int fail(int code, const std::string& msg) {
 
 #define LAUNCH_CHECK()                                                                    \
     do {                                                                                  \
-        ++g_launches;                                                                     \
+        countLaunch();                                                                    \
         cudaError_t _e = cudaGetLastError();                                              \
         if (_e != cudaSuccess) return fail(EWB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
     } while (0)
@@ -69,7 +71,7 @@ struct ewb_plan {
     int64_t nX = 0, nY = 0, nZ = 0;
     std::vector<int32_t> connHost;
     ewb::SweepPlan sweep;
-    ewb::StagedPlan staged;
+    int fusedVariant = 40404;  // row-pipelined kernel, warps 10000 P + 100 T + G; 1 = first-generation sweep (EWB_KERNEL, read once at plan creation)
 };
 
 namespace {
@@ -155,7 +157,7 @@ extern "C" {
 
 const char* ewb_last_error(void) { return g_err.c_str(); }
 int ewb_version(void) { return 100; }
-int64_t ewb_launch_count(void) { return g_launches; }
+int64_t ewb_launch_count(void) { return g_launches.load(); }
 
 int ewb_plan_create(ewb_plan** out, int el_type, int64_t n_el, int64_t n_node, const int32_t* conn_host, int device) {
     if (!out || !conn_host || n_el <= 0 || n_node <= 0) return fail(EWB_ERR_ARG, "ewb_plan_create: bad arguments");
@@ -231,7 +233,6 @@ void ewb_plan_destroy(ewb_plan* p) {
     cudaFree(p->failFlag); cudaFree(p->peScratch); cudaFree(p->vijScratch); cudaFree(p->gatherOrder); cudaFree(p->gatherSlots);
     if (p->failHost) cudaFreeHost(p->failHost);
     p->sweep.release();
-    p->staged.release();
     delete p;
 }
 
@@ -366,7 +367,14 @@ int ewb_plan_set_box(ewb_plan* p, int64_t nX, int64_t nY, int64_t nZ) {
     if (!ok) return fail(EWB_ERR_NOT_BOX, "connectivity is not BoxGen-ordered");
     p->isBox = true; p->nX = nX; p->nY = nY; p->nZ = nZ;
     if (int rc = p->sweep.build(nX, nY, nZ)) return fail(rc, "sweep plan build failed");
-    p->sweep.adjPtr = p->adjPtr;
+    if (const char* ev = getenv("EWB_KERNEL")) {  // tuning / A-B knob: "v1" or "rp<P><T><G>"
+        const std::string k(ev);
+        if (k == "v1") p->fusedVariant = 1;
+        else if (k.rfind("rp", 0) == 0) {  // rp<P>_<T>_<G>
+            int P = 4, T = 4, G = 4;
+            if (sscanf(k.c_str(), "rp%d_%d_%d", &P, &T, &G) == 3) p->fusedVariant = 10000 * P + 100 * T + G;
+        }
+    }
     return EWB_OK;
 }
 
@@ -425,19 +433,15 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
     if (int rc = materialClass(p->elType, material, props, n_props, &mp, &mc, &nms)) return rc;
 
     if (p->isBox && !(flags & EWB_FLAG_FORCE_GENERIC) && b->vij == nullptr) {
-        int launches = 0;
-        const char* pathEnv = getenv("EWB_PATH");  // "sweep" (fused) or "staged" (two streaming kernels)
-        const bool useStaged = ((flags & EWB_FLAG_STAGED) || (pathEnv && std::string(pathEnv) == "staged")) && !p->sweep.peerData;
-        if (useStaged) {
-            int rcS = p->staged.launch(p->elType, mc, p->nEl, p->nX, p->nY, p->nZ, p->conn, mp, b, p->failFlag, flags, st, &launches);
-            g_launches += launches;
-            if (rcS == EWB_OK) return EWB_OK;
-            if (rcS != EWB_ERR_UNSUPPORTED) return fail(rcS, std::string("staged launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        if (!p->sweep.indexable()) return fail(EWB_ERR_UNSUPPORTED, "ewb_assemble: the fused BoxGen kernels index nodes with int32 (3 * nodes < 2^31); use EWB_FLAG_FORCE_GENERIC");
+        const bool v1 = (flags & EWB_FLAG_SWEEP_V1) || p->fusedVariant == 1;
+        const int rc = v1 ? p->sweep.launchV1(p->elType, mc, mp, b, p->failFlag, flags, st)
+                          : ewb::launchRowPipeAny(p->sweep, p->fusedVariant, p->elType, mc, mp, b, p->failFlag, flags, st);
+        if (rc == EWB_OK) {
+            countLaunch();
+            return EWB_OK;
         }
-        int rc = p->sweep.launch(p->elType, mc, mp, b, p->failFlag, flags, st, &launches);
-        g_launches += launches;
-        if (rc == EWB_OK) return EWB_OK;
-        if (rc != EWB_ERR_UNSUPPORTED) return fail(rc, std::string("sweep launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        if (rc != EWB_ERR_UNSUPPORTED) return fail(rc, std::string("fused sweep launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     }
 
     // generic two-phase path

@@ -29,6 +29,7 @@ namespace ewb {
 struct SweepArgs {
     int nX, nY, nZ;  // elements
     int chunkLen, nChunks, tilesY, tilesZ;
+    int tileRows;  // row-pipelined kernel: node rows (y) per tile
     const double* coords;
     const double* U;
     const double* dU;
@@ -102,8 +103,9 @@ __device__ __forceinline__ int rowNode(int r) { return (0x67542310u >> (4 * r)) 
 // ---------------------------------------------------------------------------------------------
 // stg: the warp's staged nodal data [18 patch nodes][x,y,z,u0,u1,u2], already offset to this lane's element
 // (patch node of local node a = stg + (9 dx + 3 dy + dz) * 6).
-// LINEAR: stg holds the element's own 8 nodes [a][x,y,z,u0,u1,u2] instead of the 3x3x2 patch image.
-template <int MC, bool TL, bool LINEAR = false, bool HREC = false>
+// STG selects the staged image: 0 = 3x3x2 patch [X][Y][Z] (strides 9,3,1), 1 = the element's own 8 nodes [a],
+// 2 = strip of four elements along z, [X][Y][Z] with 2 x 2 x 5 nodes (strides 10,5,1; row-pipelined kernel).
+template <int MC, bool TL, int STG = 0, bool HREC = false>
 __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg, int gp, const MatParams& mp,
                                                   const double* __restrict__ state_ref, double* __restrict__ state_temp, int64_t cstride,
                                                   bool writeState, int* failFlag, long long* tsub = nullptr) {
@@ -133,7 +135,8 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
         constexpr int a = decltype(ic)::value;
         double d[3];
         shapeDeriv<8, a>(xi, eta, zeta, d);
-        constexpr int so = LINEAR ? a * 6 : (((a >> 1) & 1) * 9 + ((a >> 2) & 1) * 3 + ((a ^ (a >> 1)) & 1)) * 6;
+        constexpr int so = STG == 1 ? a * 6
+                           : (((a >> 1) & 1) * (STG == 2 ? 10 : 9) + ((a >> 2) & 1) * (STG == 2 ? 5 : 3) + ((a ^ (a >> 1)) & 1)) * 6;
         const double x0 = stg[so], x1 = stg[so + 1], x2 = stg[so + 2];
         const double u0 = stg[so + 3], u1 = stg[so + 4], u2 = stg[so + 5];
 #pragma unroll
@@ -1111,7 +1114,7 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
                 const int64_t e = ((int64_t)ex * A.nY + aey) * A.nZ + aez;
                 const int64_t off = e * 8 + agp;
                 const bool writeState = ex >= xa && apy >= 1 && apz >= 1;
-                gaussPointCompact<MC, TL, false, HREC>(rec, stage + ((ak >> 1) * 3 + (ak & 1)) * 6, agp, A.mp, A.stateRef + off, A.stateTemp + off,
+                gaussPointCompact<MC, TL, 0, HREC>(rec, stage + ((ak >> 1) * 3 + (ak & 1)) * 6, agp, A.mp, A.stateRef + off, A.stateTemp + off,
                                                        cstride, writeState, A.failFlag);
             }
             EWB_SMEM_FENCE();
@@ -1365,8 +1368,9 @@ __global__ void __launch_bounds__((((TY + 1) / 2) * ((TZ + 1) / 2) + NWP) * 32, 
 
 struct SweepPlan {
     int64_t nX = 0, nY = 0, nZ = 0;
-    const int64_t* adjPtr = nullptr;  // unused by the kernel (closed-form row bases); kept for debugging
     int nSM = 148;
+    int chunkOverride = 0;  // EWB_CHUNKS (tuning knob, read once at plan creation)
+    int spinNs = 0;         // EWB_SPIN_NS
     long long* timingBuf = nullptr;
     size_t timingCount = 0;
 
@@ -1376,18 +1380,35 @@ struct SweepPlan {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
         if (nSM <= 0) nSM = 148;
+        if (const char* ev = getenv("EWB_CHUNKS")) chunkOverride = std::max(0, atoi(ev));
+        if (const char* ev = getenv("EWB_SPIN_NS")) spinNs = atoi(ev);
         return 0;
     }
-    void release() {}
+    void release() {
+        if (timingBuf) cudaFree(timingBuf);
+        timingBuf = nullptr;
+    }
     double* peerData = nullptr;  // set by ewb_plan_set_peer
     double* peerP = nullptr;
     double* peerF = nullptr;
 
+    void fillCommon(SweepArgs& a, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags) const {
+        a.nX = (int)nX; a.nY = (int)nY; a.nZ = (int)nZ;
+        a.spinNs = spinNs;
+        a.timing = nullptr;
+        a.tileRows = 0;
+        a.coords = b->coords; a.U = b->U; a.dU = b->dU; a.stateRef = b->state_ref; a.stateTemp = b->state_temp;
+        a.data = b->csr_data; a.P = b->P; a.F = b->F; a.mp = mp; a.failFlag = failFlag;
+        a.wantK = (flags & EWB_FLAG_NO_STIFFNESS) ? 0 : 1;
+        a.accumulatePF = (flags & EWB_FLAG_ACCUMULATE_PF) ? 1 : 0;
+        a.peerData = peerData; a.peerP = peerP; a.peerF = peerF;
+    }
+
     template <int TY, int TZ>
     int fillArgs(SweepArgs& a, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st, int NW_) {
         (void)st; (void)NW_;
+        fillCommon(a, mp, b, failFlag, flags);
         const int64_t tiles = (int64_t)((nY + 1 + TY - 1) / TY) * ((nZ + 1 + TZ - 1) / TZ);
-        a.nX = (int)nX; a.nY = (int)nY; a.nZ = (int)nZ;
         a.tilesY = (int)((nY + 1 + TY - 1) / TY);
         a.tilesZ = (int)((nZ + 1 + TZ - 1) / TZ);
         // chunks along x: minimise (number of CTA rounds on nSM SMs) x (planes per chunk incl. the halo plane)
@@ -1399,39 +1420,32 @@ struct SweepPlan {
             const double cost = rounds * (double)(len + 1);
             if (cost < bestCost) { bestCost = cost; best = c; }
         }
-        if (const char* ev = getenv("EWB_CHUNKS")) best = std::max(1, atoi(ev));
-        a.spinNs = 0;
-        a.timing = nullptr;
+        if (chunkOverride > 0) best = chunkOverride;
 #ifdef EWB_TIMING
         {
-            static long long* tbuf = nullptr;
             const size_t nT = (size_t)tiles * 64 * NW_ * 12;
-            if (!tbuf) cudaMalloc((void**)&tbuf, nT * sizeof(long long));
-            cudaMemsetAsync(tbuf, 0, nT * sizeof(long long), st);
-            a.timing = tbuf;
-            timingBuf = tbuf; timingCount = nT;
+            if (timingCount < nT) {
+                if (timingBuf) cudaFree(timingBuf);
+                cudaMalloc((void**)&timingBuf, nT * sizeof(long long));
+                timingCount = nT;
+            }
+            cudaMemsetAsync(timingBuf, 0, nT * sizeof(long long), st);
+            a.timing = timingBuf;
         }
 #endif
-        if (const char* ev = getenv("EWB_SPIN_NS")) a.spinNs = atoi(ev);
         a.chunkLen = (int)((nX + 1 + best - 1) / best);
         a.nChunks = (int)((nX + 1 + a.chunkLen - 1) / a.chunkLen);
-        a.coords = b->coords; a.U = b->U; a.dU = b->dU; a.stateRef = b->state_ref; a.stateTemp = b->state_temp;
-        a.data = b->csr_data; a.P = b->P; a.F = b->F; a.mp = mp; a.failFlag = failFlag;
-        a.wantK = (flags & EWB_FLAG_NO_STIFFNESS) ? 0 : 1;
-        a.accumulatePF = (flags & EWB_FLAG_ACCUMULATE_PF) ? 1 : 0;
-        a.peerData = peerData; a.peerP = peerP; a.peerF = peerF;
         return EWB_OK;
     }
+
+    bool indexable() const { return (nX + 1) * (nY + 1) * (nZ + 1) < ((int64_t)1 << 31) / 3; }  // int32 node indexing inside the kernels
 
     template <int MC, bool TL, int TY, int TZ>
     int launchT(const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st) {
         using Rec = RecLayout<MC>;
-        constexpr int NW_ = ((TY + 1) / 2) * ((TZ + 1) / 2);
-        (void)NW_;
-        if ((nX + 1) * (nY + 1) * (nZ + 1) >= ((int64_t)1 << 31) / 3) return EWB_ERR_UNSUPPORTED;  // int32 node indexing inside the kernel
-        SweepArgs a;
-        if (int rc = fillArgs<TY, TZ>(a, mp, b, failFlag, flags, st, NW_)) return rc;
         constexpr int NW = ((TY + 1) / 2) * ((TZ + 1) / 2);
+        SweepArgs a;
+        if (int rc = fillArgs<TY, TZ>(a, mp, b, failFlag, flags, st, NW)) return rc;
         auto kern = sweepKernel<MC, TL, TY, TZ>;
         const size_t smem = ((size_t)AccLayout<TY, TZ>::TABLES + (size_t)NW * 4 * Rec::PER_EL + (size_t)NW * 108) * sizeof(double);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EWB_ERR_CUDA;
@@ -1444,7 +1458,6 @@ struct SweepPlan {
     int launchPC(const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st) {
         using Rec = RecLayout<MC>;
         constexpr int NW_ = ((TY + 1) / 2) * ((TZ + 1) / 2);
-        if ((nX + 1) * (nY + 1) * (nZ + 1) >= ((int64_t)1 << 31) / 3) return EWB_ERR_UNSUPPORTED;
         SweepArgs a;
         if (int rc = fillArgs<TY, TZ>(a, mp, b, failFlag, flags, st, NW_)) return rc;
         auto kern = sweepKernelPC<MC, TL, TY, TZ, NWP>;
@@ -1457,29 +1470,12 @@ struct SweepPlan {
         return cudaGetLastError() == cudaSuccess ? EWB_OK : EWB_ERR_CUDA;
     }
 
-    int launch(int elType, int mc, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st, int* launches) {
-        int rc = EWB_ERR_UNSUPPORTED;
-        const char* tileEnv = getenv("EWB_TILE");
-        const int tile = tileEnv ? atoi(tileEnv) : 553;  // default: producer/consumer kernel, 5x5 tile, 9 consumer + 3 producer warps
-        if (elType == EWB_C3D8 && mc == MC_LE) {
-            if (tile == 77) rc = launchT<MC_LE, false, 7, 7>(mp, b, failFlag, flags, st);
-            else if (tile == 55) rc = launchT<MC_LE, false, 5, 5>(mp, b, failFlag, flags, st);
-            else if (tile == 95) rc = launchT<MC_LE, false, 9, 5>(mp, b, failFlag, flags, st);
-            else if (tile == 57) rc = launchT<MC_LE, false, 5, 7>(mp, b, failFlag, flags, st);
-            else if (tile == 754) rc = launchPC<MC_LE, false, 7, 5, 4>(mp, b, failFlag, flags, st);
-            else if (tile == 753) rc = launchPC<MC_LE, false, 7, 5, 3>(mp, b, failFlag, flags, st);
-            else if (tile == 752) rc = launchPC<MC_LE, false, 7, 5, 2>(mp, b, failFlag, flags, st);
-            else if (tile == 75) rc = launchT<MC_LE, false, 7, 5>(mp, b, failFlag, flags, st);
-            else if (tile == 532) rc = launchPC<MC_LE, false, 5, 3, 2>(mp, b, failFlag, flags, st);
-            else if (tile == 352) rc = launchPC<MC_LE, false, 3, 5, 2>(mp, b, failFlag, flags, st);
-            else if (tile == 734) rc = launchPC<MC_LE, false, 7, 3, 4>(mp, b, failFlag, flags, st);
-            else if (tile == 553) rc = launchPC<MC_LE, false, 5, 5, 3>(mp, b, failFlag, flags, st);
-            else rc = launchPC<MC_LE, false, 5, 5, 3>(mp, b, failFlag, flags, st);
-        }
-        else if (elType == EWB_C3D8 && mc == MC_VM) rc = launchT<MC_VM, false, 7, 5>(mp, b, failFlag, flags, st);
-        else if (elType == EWB_C3D8TL && mc == MC_NH) rc = launchT<MC_NH, true, 7, 5>(mp, b, failFlag, flags, st);
-        if (rc == EWB_OK) *launches = 1;
-        return rc;
+    // first-generation fused sweep (colour-ordered shared-memory accumulation)
+    int launchV1(int elType, int mc, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st) {
+        if (elType == EWB_C3D8 && mc == MC_LE) return launchPC<MC_LE, false, 5, 5, 3>(mp, b, failFlag, flags, st);
+        if (elType == EWB_C3D8 && mc == MC_VM) return launchT<MC_VM, false, 7, 5>(mp, b, failFlag, flags, st);
+        if (elType == EWB_C3D8TL && mc == MC_NH) return launchT<MC_NH, true, 7, 5>(mp, b, failFlag, flags, st);
+        return EWB_ERR_UNSUPPORTED;
     }
 };
 

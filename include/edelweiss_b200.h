@@ -66,7 +66,7 @@ enum {
     EWB_FLAG_ACCUMULATE_PF = 1, /* P += , F += (reference semantics on a caller-zeroed vector); default overwrites */
     EWB_FLAG_FORCE_GENERIC = 2, /* use the two-phase VIJ path even when a structured (BoxGen) plan exists */
     EWB_FLAG_NO_STIFFNESS = 4,  /* residual / state only (P, F, stateTemp) */
-    EWB_FLAG_STAGED = 8         /* BoxGen plans: two streaming kernels (symmetric-half element blocks, then an ordered gather) instead of the fused sweep */
+    EWB_FLAG_SWEEP_V1 = 8       /* BoxGen plans: the first-generation fused sweep (colour-ordered shared-memory accumulation) instead of the row-pipelined gather sweep */
 };
 
 typedef struct ewb_plan ewb_plan; /* opaque: mesh topology + CSR slot tables on one device */

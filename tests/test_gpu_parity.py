@@ -71,7 +71,7 @@ def test_golden(name, path):
         ("C3D20", "vonmises", [2.1e4, 0.22, 355, 1000, 200, 1400], (3, 3, 4), 5e-3),
     ],
 )
-@pytest.mark.parametrize("path", ["generic", "auto", "staged"])
+@pytest.mark.parametrize("path", ["generic", "auto", "sweepv1"])
 def test_against_oracle_seeded(elType, material, props, n, scale, path):
     import torch
 
@@ -88,7 +88,7 @@ def test_against_oracle_seeded(elType, material, props, n, scale, path):
     if nn == 8:
         coords = coords + 0.15 * rng.uniform(-1, 1, coords.shape)
     asm = ElementAssembly(elType, conn, coords, material, props, box=n if path != "generic" else None)
-    flags = {"generic": _lib.EWB_FLAG_FORCE_GENERIC, "auto": 0, "staged": _lib.EWB_FLAG_STAGED}[path]
+    flags = {"generic": _lib.EWB_FLAG_FORCE_GENERIC, "auto": 0, "sweepv1": _lib.EWB_FLAG_SWEEP_V1}[path]
     nGp = 27 if nn == 20 else 8
     state = np.zeros((conn.shape[0], nGp, 12 + port.MATERIAL_NSTATE[material]))
     U = np.zeros(3 * coords.shape[0])
@@ -312,7 +312,7 @@ def test_full_size_properties(workload):
 
 @pytest.mark.parametrize("n", [(1, 1, 1), (1, 1, 6), (2, 1, 1), (1, 7, 1), (6, 2, 13), (13, 6, 2), (35, 3, 3), (8, 15, 11)])
 @pytest.mark.parametrize("material", ["linearelastic", "vonmises"])
-@pytest.mark.parametrize("path", ["sweep", "staged"])
+@pytest.mark.parametrize("path", ["sweep", "sweepv1"])
 def test_sweep_edge_shapes(n, material, path):
     """Degenerate and ragged boxes: tiles larger than the mesh, single element planes, several x-chunks,
     tile edges that coincide with the mesh boundary (producer/consumer and single-role kernels)."""
@@ -336,7 +336,7 @@ def test_sweep_edge_shapes(n, material, path):
     asm.state_temp.fill_(float("nan"))
     from edelweissfe_b200 import _lib
 
-    asm.assemble(_lib.EWB_FLAG_STAGED if path == "staged" else 0)
+    asm.assemble(_lib.EWB_FLAG_SWEEP_V1 if path == "sweepv1" else 0)
     asm.poll()
     state = np.zeros((conn.shape[0], 8, 12 + port.MATERIAL_NSTATE[material]))
     o = port.assemble("C3D8", material, props, coords, conn, dU, dU, state, want_vij=False)

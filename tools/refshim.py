@@ -1,8 +1,9 @@
 """Bootstrap to import the UNMODIFIED EdelweissFE reference from /root/reference in this
 container (it is Python; missing optional deps are stubbed in sys.modules, nothing is
-copied or edited).  Used ONLY by tests/golden/make_golden.py (fixture generation) and by
-the CPU-side plugin tests that are skipped when the reference tree is absent.  Never
-imported by the product path, smoke() or bench.py (the GPU box has no /root/reference).
+copied or edited).  Used by tests/golden/make_golden.py (fixture generation), by the plugin tests (CPU: oracle-backed
+stand-in; GPU box: the CUDA backend) and by bench.py's reference arm.  The tree is looked up at
+baseline/_ref (tools/install_reference.py — git-ignored, travels with gpurun) and then at
+/root/reference (build container only).  Never imported by the product path or smoke().
 
 Recipe follows SURVEY.md Appendix B.
 """
@@ -10,7 +11,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("EDELWEISS_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_INSTALLED = os.path.join(_REPO, "baseline", "_ref")  # tools/install_reference.py (travels to the GPU box, git-ignored)
+
+
+def _default_root():
+    if os.path.isdir(os.path.join(_INSTALLED, "edelweissfe")):
+        return _INSTALLED
+    return "/root/reference"
+
+
+REFERENCE_ROOT = os.environ.get("EDELWEISS_REFERENCE_ROOT") or _default_root()
 
 
 def reference_available() -> bool:
@@ -104,6 +115,11 @@ def build_cython_module(relpath: str, modname: str, openmp: bool = False):
 
     if modname in sys.modules:
         return sys.modules[modname]
+    prebuilt = os.path.join(REFERENCE_ROOT, os.path.splitext(relpath)[0] + sysconfig.get_config_var("EXT_SUFFIX"))
+    if os.path.exists(prebuilt):  # installed tree (tools/install_reference.py): the module imports like any other
+        import importlib
+
+        return importlib.import_module(modname)
     out = os.environ.get("EWB_REFBUILD_DIR", "/tmp/ewb_refbuild")
     os.makedirs(out, exist_ok=True)
     base = modname.split(".")[-1]
