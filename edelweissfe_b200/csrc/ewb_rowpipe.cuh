@@ -92,8 +92,11 @@ struct RowPipeLayout {
     static_assert(NE % 4 == 0, "a row is processed in strips of four elements");
 };
 
-template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW>
+// RP/RT/RG > 0: per-role register budgets (setmaxnreg, warp groups of four warps: NPW, NTW, NGW must be multiples of 4)
+template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0>
 __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const SweepArgs A) {
+    static_assert(RP == 0 || (NPW % 4 == 0 && NTW % 4 == 0 && NGW % 4 == 0), "setmaxnreg works on warp groups");
+    constexpr int REG0 = (65536 / ((NPW + NTW + NGW) * 32)) / 8 * 8;  // registers per thread at launch
     using L = RowPipeLayout<MC, TL, TZ, NPW>;
     using R = RecLayout<MC>;
     constexpr int NE = L::NE, PEL = L::PEL, SLOT_EL = L::SLOT_EL;
@@ -146,6 +149,10 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
     const int64_t cstride = (int64_t)A.nX * A.nY * A.nZ * 8;
 
     if (warp < NPW) {
+        if constexpr (RP > 0) {
+            if constexpr (RP >= REG0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RP));
+            else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RP));
+        }
         // ===================== P warps: phase A, strips of four elements =====================
         const double* __restrict__ uSrc = TL ? A.U : A.dU;
         double* stageBuf = smem + L::OFF_STAGE + warp * 2 * L::STAGE_EL;
@@ -216,6 +223,10 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
     }
 
     if (warp < NPW + NTW) {
+        if constexpr (RT > 0) {
+            if constexpr (RT >= REG0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RT));
+            else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RT));
+        }
         // ===================== T warps: stiffness blocks of one element per warp, into the row's slot ring =====================
         const int tw = warp - NPW;
         const int bRow = lane >> 2, bq = lane & 3;
@@ -295,6 +306,10 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
     }
 
     // ===================== G warps: per node column, gather the row pair's elements and store the finished rows =====================
+    if constexpr (RG > 0) {
+        if constexpr (RG >= REG0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RG));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RG));
+    }
     const int gw = warp - NPW - NTW;
     auto pre = [](int i) { return i == 0 ? 0 : 3 * i - 1; };
     const int totY = 3 * NY - 2, totZ = 3 * NZ - 2;
@@ -521,7 +536,7 @@ inline RowPipeTiling rowPipeTiling(int64_t nX, int64_t nY, int64_t nZ, int nSM, 
     return best;
 }
 
-template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW>
+template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0>
 int launchRowPipe(SweepPlan& sp, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st) {
     using L = RowPipeLayout<MC, TL, TZ, NPW>;
     constexpr int SMEM_MAX = 232448;
@@ -544,7 +559,7 @@ int launchRowPipe(SweepPlan& sp, const MatParams& mp, const ewb_buffers* b, int*
         a.timing = sp.timingBuf;
     }
 #endif
-    auto kern = rowPipeKernel<MC, TL, TZ, NPW, NTW, NGW>;
+    auto kern = rowPipeKernel<MC, TL, TZ, NPW, NTW, NGW, RP, RT, RG>;
     const size_t smem = ((size_t)L::fixedDoubles() + (size_t)L::carryDoubles(t.tileRows)) * sizeof(double);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EWB_ERR_CUDA;
     kern<<<(unsigned)grid, (NPW + NTW + NGW) * 32, smem, st>>>(a);
@@ -562,6 +577,9 @@ int launchRowPipeVariant(SweepPlan& sp, int variant, const MatParams& mp, const 
         case 20406: return launchRowPipe<MC, TL, 7, 2, 4, 6>(sp, mp, b, failFlag, flags, st);
         case 30405: return launchRowPipe<MC, TL, 7, 3, 4, 5>(sp, mp, b, failFlag, flags, st);
         case 30803: return launchRowPipe<MC, TL, 7, 3, 8, 3>(sp, mp, b, failFlag, flags, st);
+        case 1040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120>(sp, mp, b, failFlag, flags, st);
+        case 1040408: return launchRowPipe<MC, TL, 7, 4, 4, 8, 168, 168, 88>(sp, mp, b, failFlag, flags, st);
+        case 1040808: return launchRowPipe<MC, TL, 7, 4, 8, 8, 152, 104, 72>(sp, mp, b, failFlag, flags, st);
 #endif
         case 40404:
         default: return launchRowPipe<MC, TL, 7, 4, 4, 4>(sp, mp, b, failFlag, flags, st);
