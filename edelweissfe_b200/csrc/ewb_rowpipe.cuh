@@ -579,7 +579,6 @@ int launchRowPipeVariant(SweepPlan& sp, int variant, const MatParams& mp, const 
         case 30803: return launchRowPipe<MC, TL, 7, 3, 8, 3>(sp, mp, b, failFlag, flags, st);
         case 1040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120>(sp, mp, b, failFlag, flags, st);
         case 1040408: return launchRowPipe<MC, TL, 7, 4, 4, 8, 168, 168, 88>(sp, mp, b, failFlag, flags, st);
-        case 1040808: return launchRowPipe<MC, TL, 7, 4, 8, 8, 152, 104, 72>(sp, mp, b, failFlag, flags, st);
 #endif
         case 40404:
         default: return launchRowPipe<MC, TL, 7, 4, 4, 4>(sp, mp, b, failFlag, flags, st);
