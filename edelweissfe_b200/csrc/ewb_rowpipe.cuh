@@ -70,14 +70,14 @@ __device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity, volatil
 #define RP_FLUSH(cnt)
 #endif
 
-template <int MC, bool TL, int TZ, int NPW>
+template <int MC, bool TL, int TZ, int NPW, int RECST = 2>
 struct RowPipeLayout {
     static constexpr int NE = TZ + 1;  // elements per row (incl. halo)
     static constexpr bool HREC = (MC == MC_LE) && !TL;
     static constexpr int PEL = HREC ? RecLayoutH::PER_EL : RecLayout<MC>::PER_EL;
     static constexpr int SLOT_EL = 600;  // 576 stiffness-block doubles [lane][18] + 24 residual doubles [row][3]
     static constexpr int SLOT_STAGES = 3;
-    static constexpr int REC_STAGES = 2;
+    static constexpr int REC_STAGES = RECST;
     static constexpr int STAGE_EL = 120;  // 2 x 2 x 5 nodes x (x,y,z,u0,u1,u2)
     static constexpr int OFF_SLOTS = 0;
     static constexpr int OFF_REC = OFF_SLOTS + SLOT_STAGES * NE * SLOT_EL;
@@ -93,11 +93,11 @@ struct RowPipeLayout {
 };
 
 // RP/RT/RG > 0: per-role register budgets (setmaxnreg, warp groups of four warps: NPW, NTW, NGW must be multiples of 4)
-template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0>
+template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0, int RECST = 2>
 __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const SweepArgs A) {
     static_assert(RP == 0 || (NPW % 4 == 0 && NTW % 4 == 0 && NGW % 4 == 0), "setmaxnreg works on warp groups");
     constexpr int REG0 = (65536 / ((NPW + NTW + NGW) * 32)) / 8 * 8;  // registers per thread at launch
-    using L = RowPipeLayout<MC, TL, TZ, NPW>;
+    using L = RowPipeLayout<MC, TL, TZ, NPW, RECST>;
     using R = RecLayout<MC>;
     constexpr int NE = L::NE, PEL = L::PEL, SLOT_EL = L::SLOT_EL;
     constexpr bool HREC = L::HREC;
@@ -160,15 +160,24 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
         const int ak = lane >> 3, agp = lane & 7;
         const int nTasks = nRows * HALVES;
         constexpr int NST = 12 + (MC != MC_LE ? 1 : 0);
-        auto issue = [&](int t, int par) {
-            if (t < nTasks) {
-                const int n = t / HALVES, h = t - n * HALVES;
-                const int s = n / rowsPerStep, jj = n - s * rowsPerStep;
-                const int exs = exBegin + s, ey = y0 - 1 + jj;
+        // task t = (row n, strip h); this warp's tasks are t = warp, warp + NPW, ...  The decoded position of the task being
+        // computed (c*) and of the one whose nodal data is being fetched (f*) advance incrementally: no divisions in the loop.
+        struct Pos { int n, h, s, jj; };
+        auto advance = [&](Pos& p) {
+            const int hn = p.h + NPW;
+            const int dn = hn / HALVES;
+            p.h = hn % HALVES;
+            p.n += dn;
+            p.jj += dn;
+            while (p.jj >= rowsPerStep) { p.jj -= rowsPerStep; ++p.s; }
+        };
+        auto issue = [&](const Pos& p, int par) {
+            if (p.n < nRows) {
+                const int exs = exBegin + p.s, ey = y0 - 1 + p.jj;
                 if (ey >= 0 && ey < A.nY) {
                     if (lane < 20) {
                         const int X = lane / 10, Y = (lane / 5) & 1, Z = lane % 5;
-                        const int iy = ey + Y, iz = z0 - 1 + 4 * h + Z;
+                        const int iy = ey + Y, iz = z0 - 1 + 4 * p.h + Z;
                         if (iz >= 0 && iz < NZ) {
                             const int64_t o = 3 * (((int64_t)(exs + X) * NY + iy) * NZ + iz);
                             const unsigned dst = stageAddr0 + (unsigned)par * (L::STAGE_EL * 8u) + 48u * lane;
@@ -179,26 +188,31 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
                             }
                         }
                     }
-                    const int k = 4 * h + ak, ez = z0 - 1 + k;
+#ifndef EWB_NO_STATE_PREFETCH
+                    const int k = 4 * p.h + ak, ez = z0 - 1 + k;
                     if (ez >= 0 && ez < A.nZ && k <= nz) {
                         const double* sp = A.stateRef + (((int64_t)exs * A.nY + ey) * A.nZ + ez) * 8 + agp;
 #pragma unroll
                         for (int c = 0; c < NST; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + c * cstride));
                     }
+#endif
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         int par = 0;
         RP_DECL();
-        issue(warp, par);
+        Pos cur{warp / HALVES, warp % HALVES, 0, warp / HALVES};
+        while (cur.jj >= rowsPerStep) { cur.jj -= rowsPerStep; ++cur.s; }
+        Pos nxt = cur;
+        issue(cur, par);
 #pragma unroll 1
-        for (int t = warp; t < nTasks; t += NPW, par ^= 1) {
+        for (; cur.n < nRows; par ^= 1) {
             RP_T0();
-            issue(t + NPW, par ^ 1);
-            const int n = t / HALVES, h = t - n * HALVES;
-            const int s = n / rowsPerStep, jj = n - s * rowsPerStep;
-            const int ex = exBegin + s, ey = y0 - 1 + jj;
+            advance(nxt);
+            issue(nxt, par ^ 1);
+            const int n = cur.n, h = cur.h, jj = cur.jj;
+            const int ex = exBegin + cur.s, ey = y0 - 1 + jj;
             const int rs = n % L::REC_STAGES;
             RP_LAP(2);
             mbarWait(recEmpty + rs, ((n / L::REC_STAGES) & 1) ^ 1, abortFlag, A.failFlag);
@@ -217,6 +231,7 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
             __syncwarp();
             mbarArrive(recFull + rs);
             RP_LAP(3);
+            cur = nxt;
         }
         RP_FLUSH(nTasks);
         return;
@@ -536,9 +551,9 @@ inline RowPipeTiling rowPipeTiling(int64_t nX, int64_t nY, int64_t nZ, int nSM, 
     return best;
 }
 
-template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0>
+template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0, int RECST = 2>
 int launchRowPipe(SweepPlan& sp, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st) {
-    using L = RowPipeLayout<MC, TL, TZ, NPW>;
+    using L = RowPipeLayout<MC, TL, TZ, NPW, RECST>;
     constexpr int SMEM_MAX = 232448;
     const int rowsMax = (SMEM_MAX / 8 - L::fixedDoubles()) / (TZ * L::CARRY_COL);
     if (rowsMax < 1) return EWB_ERR_UNSUPPORTED;
@@ -559,7 +574,7 @@ int launchRowPipe(SweepPlan& sp, const MatParams& mp, const ewb_buffers* b, int*
         a.timing = sp.timingBuf;
     }
 #endif
-    auto kern = rowPipeKernel<MC, TL, TZ, NPW, NTW, NGW, RP, RT, RG>;
+    auto kern = rowPipeKernel<MC, TL, TZ, NPW, NTW, NGW, RP, RT, RG, RECST>;
     const size_t smem = ((size_t)L::fixedDoubles() + (size_t)L::carryDoubles(t.tileRows)) * sizeof(double);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EWB_ERR_CUDA;
     kern<<<(unsigned)grid, (NPW + NTW + NGW) * 32, smem, st>>>(a);
@@ -578,6 +593,8 @@ int launchRowPipeVariant(SweepPlan& sp, int variant, const MatParams& mp, const 
         case 30405: return launchRowPipe<MC, TL, 7, 3, 4, 5>(sp, mp, b, failFlag, flags, st);
         case 30803: return launchRowPipe<MC, TL, 7, 3, 8, 3>(sp, mp, b, failFlag, flags, st);
         case 1040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120>(sp, mp, b, failFlag, flags, st);
+        case 2040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120, 3>(sp, mp, b, failFlag, flags, st);
+        case 2040404: return launchRowPipe<MC, TL, 7, 4, 4, 4, 0, 0, 0, 3>(sp, mp, b, failFlag, flags, st);
         case 1040408: return launchRowPipe<MC, TL, 7, 4, 4, 8, 168, 168, 88>(sp, mp, b, failFlag, flags, st);
 #endif
         case 40404:
