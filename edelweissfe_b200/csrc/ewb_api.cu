@@ -71,7 +71,7 @@ struct ewb_plan {
     int64_t nX = 0, nY = 0, nZ = 0;
     std::vector<int32_t> connHost;
     ewb::SweepPlan sweep;
-    int fusedVariant = 40404;  // row-pipelined kernel, warps 10000 P + 100 T + G; 1 = first-generation sweep (EWB_KERNEL, read once at plan creation)
+    int fusedVariant = 2040804;  // row-pipelined kernel, warps 10000 P + 100 T + G; 1 = first-generation sweep (EWB_KERNEL, read once at plan creation)
 };
 
 namespace {
@@ -372,7 +372,9 @@ int ewb_plan_set_box(ewb_plan* p, int64_t nX, int64_t nY, int64_t nZ) {
         if (k == "v1") p->fusedVariant = 1;
         else if (k.rfind("rp", 0) == 0) {  // rp<P>_<T>_<G>
             int P = 4, T = 4, G = 4;
-            if (sscanf(k.c_str(), "rpr%d_%d_%d", &P, &T, &G) == 3) p->fusedVariant = 2000000 + 10000 * P + 100 * T + G;  // 3 record stages
+            if (sscanf(k.c_str(), "rpa%d_%d_%d", &P, &T, &G) == 3) p->fusedVariant = 3000000 + 10000 * P + 100 * T + G;  // register split a
+            else if (sscanf(k.c_str(), "rpb%d_%d_%d", &P, &T, &G) == 3) p->fusedVariant = 4000000 + 10000 * P + 100 * T + G;  // register split b
+            else if (sscanf(k.c_str(), "rpr%d_%d_%d", &P, &T, &G) == 3) p->fusedVariant = 2000000 + 10000 * P + 100 * T + G;  // 3 record stages
             else if (sscanf(k.c_str(), "rps%d_%d_%d", &P, &T, &G) == 3) p->fusedVariant = 1000000 + 10000 * P + 100 * T + G;  // with per-role register budgets
             else if (sscanf(k.c_str(), "rp%d_%d_%d", &P, &T, &G) == 3) p->fusedVariant = 10000 * P + 100 * T + G;
         }

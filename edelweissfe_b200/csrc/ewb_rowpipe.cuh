@@ -103,6 +103,10 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
     constexpr bool HREC = L::HREC;
     constexpr int NT = (NPW + NTW + NGW) * 32;
     constexpr int HALVES = NE / 4;
+    // y-chaining: with one T warp per element position, the warp adds the previous element row's blocks of the shared y-face
+    // to this row's (registers), so that the gather reads every (column, neighbour) pair from ONE element row.  Odd element
+    // rows use the row index with the y bit inverted (flip), which puts the shared face at the same fragment positions.
+    constexpr bool CHAIN = (NTW == NE);
 
     extern __shared__ double smem[];
     double* slots = smem + L::OFF_SLOTS;
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
                 const int64_t off = (((int64_t)ex * A.nY + ey) * A.nZ + ez) * 8 + agp;
                 const bool writeState = ex >= xa && jj >= 1 && k >= 1;
                 gaussPointCompact<MC, TL, 2, HREC>(rec, stageBuf + par * L::STAGE_EL + ak * 6, agp, A.mp, A.stateRef + off, A.stateTemp + off, cstride,
-                                                   writeState, A.failFlag);
+                                                   writeState, A.failFlag, nullptr, CHAIN ? 16 * (jj & 1) : 0);
             }
             __syncwarp();
             mbarArrive(recFull + rs);
@@ -246,8 +250,8 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
         const int tw = warp - NPW;
         const int bRow = lane >> 2, bq = lane & 3;
         double dNl[2][3];
-        if constexpr (!HREC) {
-            const int na = rowNode(bRow);
+        auto setShapeDerivs = [&](int flip) {  // lane-constant dN of the lane's row node (rows of flipped element rows have the y bit inverted)
+            const int na = rowNode(bRow ^ (flip << 2));
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 double xi, eta, zeta, w;
@@ -258,7 +262,11 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
                 dNl[ks][1] = 0.125 * sa * fe * fz;
                 dNl[ks][2] = 0.125 * sc * fx * fe;
             }
-        }
+        };
+        if constexpr (!HREC) setShapeDerivs(0);
+        double Kp0[9], Kp1[9];  // CHAIN: the previous element row's blocks of this warp's element position
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Kp0[i] = Kp1[i] = 0.0;
         const bool wantK = A.wantK != 0;
         RP_DECL();
 #pragma unroll 1
@@ -270,6 +278,8 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
             mbarWait(recFull + rs, (n / L::REC_STAGES) & 1, abortFlag, A.failFlag);
             RP_LAP(0);
             bool slotReady = false;
+            const int flip = CHAIN ? (jj & 1) : 0;
+            if constexpr (CHAIN && !HREC) setShapeDerivs(flip);
 #pragma unroll
             for (int k = tw; k < NE; k += NTW) {
                 const int ez = z0 - 1 + k;
@@ -282,6 +292,19 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
                     else elementTiles<MC>(T, lane, dNl, A.mp, wantK, acc, Pr);
                     finishBlock<MC>(acc, 0, A.mp, K0);
                     finishBlock<MC>(acc, 1, A.mp, K1);
+                }
+                if constexpr (CHAIN) {
+                    if (valid) {
+                        if (jj != 0 && (bRow >> 2) == flip && (bq >> 1) == flip) {  // both nodes on the face shared with the previous row
+#pragma unroll
+                            for (int i = 0; i < 9; ++i) { K0[i] += Kp0[i]; K1[i] += Kp1[i]; }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) { Kp0[i] = K0[i]; Kp1[i] = K1[i]; }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) Kp0[i] = Kp1[i] = 0.0;
+                    }
                 }
                 if (!slotReady) {
                     RP_LAP(2);
@@ -341,6 +364,18 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
         const bool act = lane < 27 && by >= 0 && by <= 1 && bz >= 0 && bz <= 1;
         cbase[c] = act ? (8 * (4 * py + pz) + (4 * by + bz)) * 9 + jc : -1;
     }
+    // CHAIN: the element row that holds the lane's neighbour is fixed by dy (dy = -1: row below, else the row above, which carries the
+    // chained sum for dy = 0); per flip parity f of the upper row and per z-colour: offset of block (a_lo, b_lo)[0][jc], -1 = not held
+    int cbz[2][2];
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+#pragma unroll
+        for (int cz = 0; cz < 2; ++cz) {
+            const int pz = 1 - cz, bz = pz + dz;
+            const bool act = lane < 27 && bz >= 0 && bz <= 1;
+            const int rowA = 4 * f + pz, rowB = (dy == 0 ? 4 * f : 4 * (1 - f)) + bz;
+            cbz[f][cz] = act ? (8 * rowA + rowB) * 9 + jc : -1;
+        }
     // residual pass (one warp per row): lane < 3 TZ owns (column lane / 3, component lane % 3)
     const int pfCol = lane / 3, pfi = lane - 3 * pfCol;
     const bool wantK = A.wantK != 0;
@@ -365,7 +400,8 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
         const double* rowLo = slots + (size_t)(ssPrev * NE) * SLOT_EL;  // element row iy - 1 (colours cy = 0)
         const double* rowHi = slots + (size_t)(ss * NE) * SLOT_EL;      // element row iy     (colours cy = 1)
         // x- and y-interior row of an interior plane step: every column with an interior z takes the lean path
-        const bool leanRow = wantK && loOwned && hiOwned && ex >= 1 && ex + 1 <= NX - 2 && iy >= 1 && iy <= NY - 2;
+        const bool leanRow = wantK && ex >= 1 && ex + 1 <= NX - 2 && iy >= 1 && iy <= NY - 2;
+        const int flip = jj & 1;  // CHAIN: flip parity of the upper element row (the lower one has the opposite parity)
         double* leanBase = A.data + (9 * (int64_t)(3 * ex - 1) * totYZ + 27 * ((int64_t)(3 * iy - 1) * totZ - 3) + lane);
         const int64_t nextPlane = 27 * totYZ;
         // columns of this warp: (ly * TZ + lzz) % NGW == gw
@@ -378,31 +414,52 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
                 // ---- lean path: all four elements exist, the 9 sub-row pieces of the column are 27-double runs at base + m * 27.
                 // Branch-free: a lane whose neighbour is not in colour c's element reads zeros, so all 48 loads are independent. ----
                 if (lane < 27) {
-                    const double* e0 = cbase[0] >= 0 ? rowLo + lzz * SLOT_EL + cbase[0] : zeroPad;
-                    const double* e1 = cbase[1] >= 0 ? rowLo + (lzz + 1) * SLOT_EL + cbase[1] : zeroPad;
-                    const double* e2 = cbase[2] >= 0 ? rowHi + lzz * SLOT_EL + cbase[2] : zeroPad;
-                    const double* e3 = cbase[3] >= 0 ? rowHi + (lzz + 1) * SLOT_EL + cbase[3] : zeroPad;
                     double v[2][2][3];
+                    if constexpr (CHAIN) {
+                        const double* rowSel = (dy == -1 ? rowLo : rowHi) + lzz * SLOT_EL;
+                        const int c0 = flip ? cbz[1][0] : cbz[0][0], c1 = flip ? cbz[1][1] : cbz[0][1];
+                        const double* e0 = c0 >= 0 ? rowSel + c0 : zeroPad;
+                        const double* e1 = c1 >= 0 ? rowSel + SLOT_EL + c1 : zeroPad;
 #pragma unroll
-                    for (int a = 0; a < 2; ++a)
+                        for (int a = 0; a < 2; ++a)
 #pragma unroll
-                        for (int b = 0; b < 2; ++b)
+                            for (int b = 0; b < 2; ++b)
 #pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                const int o = 144 * a + 18 * b + 3 * i;
-                                v[a][b][i] = (e0[o] + e1[o]) + (e2[o] + e3[o]);
-                            }
+                                for (int i = 0; i < 3; ++i) {
+                                    const int o = 144 * a + 18 * b + 3 * i;
+                                    v[a][b][i] = e0[o] + e1[o];
+                                }
+                    } else {
+                        const double* e0 = cbase[0] >= 0 ? rowLo + lzz * SLOT_EL + cbase[0] : zeroPad;
+                        const double* e1 = cbase[1] >= 0 ? rowLo + (lzz + 1) * SLOT_EL + cbase[1] : zeroPad;
+                        const double* e2 = cbase[2] >= 0 ? rowHi + lzz * SLOT_EL + cbase[2] : zeroPad;
+                        const double* e3 = cbase[3] >= 0 ? rowHi + (lzz + 1) * SLOT_EL + cbase[3] : zeroPad;
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) v[0][0][i] += cc[27 * i + lane];
+                        for (int a = 0; a < 2; ++a)
+#pragma unroll
+                            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                                for (int i = 0; i < 3; ++i) {
+                                    const int o = 144 * a + 18 * b + 3 * i;
+                                    v[a][b][i] = (e0[o] + e1[o]) + (e2[o] + e3[o]);
+                                }
+                    }
                     RP_LAP(1);
                     double* ptr = leanBase + 243 * (int64_t)iz;
                     double* ptrN = ptr + nextPlane;
+                    if (loOwned) {
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        ptrN[(3 * i) * 27] = v[1][0][i];
-                        ptr[(3 * i + 1) * 27] = v[0][0][i];
-                        ptr[(3 * i + 2) * 27] = v[0][1][i];
-                        cc[27 * i + lane] = v[1][1][i];
+                        for (int i = 0; i < 3; ++i) {
+                            ptr[(3 * i + 1) * 27] = v[0][0][i] + cc[27 * i + lane];
+                            ptr[(3 * i + 2) * 27] = v[0][1][i];
+                        }
+                    }
+                    if (hiOwned) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            ptrN[(3 * i) * 27] = v[1][0][i];
+                            cc[27 * i + lane] = v[1][1][i];
+                        }
                     }
                     RP_LAP(2);
                 }
@@ -415,19 +472,40 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
             for (int a = 0; a < 2; ++a)
 #pragma unroll
                 for (int b = 0; b < 2; ++b) v[a][b][0] = v[a][b][1] = v[a][b][2] = 0.0;
+            if constexpr (CHAIN) {
+                // the lane's source row: below for dy = -1, above otherwise — except on the top face of the box (no element row
+                // above), where the dy = 0 blocks are the lower row's own y-face blocks (same offsets, see cbz)
+                const bool useLo = dy == -1 || !vy1;
+                const bool rowOk = dy == -1 ? vy0 : (dy == 1 ? vy1 : true);
+                const double* rowSel = (useLo ? rowLo : rowHi) + lzz * SLOT_EL;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int cy = c >> 1, cz = c & 1;
-                const bool cv = (cy ? vy1 : vy0) && (cz ? vz1 : vz0);  // warp uniform
-                if (!cv) continue;
-                if (wantK && cbase[c] >= 0) {
-                    const double* eb = (cy ? rowHi : rowLo) + (lzz + cz) * SLOT_EL + cbase[c];
+                for (int cz = 0; cz < 2; ++cz) {
+                    const int cb = flip ? cbz[1][cz] : cbz[0][cz];
+                    if (wantK && rowOk && (cz ? vz1 : vz0) && cb >= 0) {
+                        const double* eb = rowSel + cz * SLOT_EL + cb;
 #pragma unroll
-                    for (int a = 0; a < 2; ++a)
+                        for (int a = 0; a < 2; ++a)
 #pragma unroll
-                        for (int b = 0; b < 2; ++b)
+                            for (int b = 0; b < 2; ++b)
 #pragma unroll
-                            for (int i = 0; i < 3; ++i) v[a][b][i] += eb[144 * a + 18 * b + 3 * i];
+                                for (int i = 0; i < 3; ++i) v[a][b][i] += eb[144 * a + 18 * b + 3 * i];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int cy = c >> 1, cz = c & 1;
+                    const bool cv = (cy ? vy1 : vy0) && (cz ? vz1 : vz0);  // warp uniform
+                    if (!cv) continue;
+                    if (wantK && cbase[c] >= 0) {
+                        const double* eb = (cy ? rowHi : rowLo) + (lzz + cz) * SLOT_EL + cbase[c];
+#pragma unroll
+                        for (int a = 0; a < 2; ++a)
+#pragma unroll
+                            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                                for (int i = 0; i < 3; ++i) v[a][b][i] += eb[144 * a + 18 * b + 3 * i];
+                    }
                 }
             }
             // outputs of this column: node plane ex (rows dx = 0, +1) and node plane ex + 1 (dx = -1; carry)
@@ -479,7 +557,9 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
             for (int c = 0; c < 4; ++c) {
                 const int cy = c >> 1, cz = c & 1;
                 if ((cy ? vy1 : vy0) && (cz ? vz1 : vz0)) {
-                    const double* e = (cy ? rowHi : rowLo) + (pfCol + cz) * SLOT_EL + 576 + 3 * (4 * (1 - cy) + (1 - cz)) + pfi;
+                    // fragment row of the column's node in element (cy, cz); CHAIN: rows of flipped element rows have the y bit inverted
+                    const int fr = CHAIN ? 4 * flip + (1 - cz) : 4 * (1 - cy) + (1 - cz);
+                    const double* e = (cy ? rowHi : rowLo) + (pfCol + cz) * SLOT_EL + 576 + 3 * fr + pfi;
                     const double plo = e[0], phi = e[6];
                     pl += plo; fl += fabs(plo);
                     ph += phi; fh += fabs(phi);
@@ -587,18 +667,15 @@ int launchRowPipeVariant(SweepPlan& sp, int variant, const MatParams& mp, const 
     switch (variant) {
 #ifdef EWB_VARIANTS
         case 40804: return launchRowPipe<MC, TL, 7, 4, 8, 4>(sp, mp, b, failFlag, flags, st);
-        case 20804: return launchRowPipe<MC, TL, 7, 2, 8, 4>(sp, mp, b, failFlag, flags, st);
-        case 20803: return launchRowPipe<MC, TL, 7, 2, 8, 3>(sp, mp, b, failFlag, flags, st);
-        case 20406: return launchRowPipe<MC, TL, 7, 2, 4, 6>(sp, mp, b, failFlag, flags, st);
         case 30405: return launchRowPipe<MC, TL, 7, 3, 4, 5>(sp, mp, b, failFlag, flags, st);
-        case 30803: return launchRowPipe<MC, TL, 7, 3, 8, 3>(sp, mp, b, failFlag, flags, st);
         case 1040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120>(sp, mp, b, failFlag, flags, st);
-        case 2040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120, 3>(sp, mp, b, failFlag, flags, st);
         case 2040404: return launchRowPipe<MC, TL, 7, 4, 4, 4, 0, 0, 0, 3>(sp, mp, b, failFlag, flags, st);
-        case 1040408: return launchRowPipe<MC, TL, 7, 4, 4, 8, 168, 168, 88>(sp, mp, b, failFlag, flags, st);
+        case 3040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 120, 104, 3>(sp, mp, b, failFlag, flags, st);
+        case 4040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 152, 128, 104, 3>(sp, mp, b, failFlag, flags, st);
 #endif
-        case 40404:
-        default: return launchRowPipe<MC, TL, 7, 4, 4, 4>(sp, mp, b, failFlag, flags, st);
+        case 40404: return launchRowPipe<MC, TL, 7, 4, 4, 4>(sp, mp, b, failFlag, flags, st);
+        case 2040804:
+        default: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120, 3>(sp, mp, b, failFlag, flags, st);
     }
 }
 

@@ -108,7 +108,7 @@ __device__ __forceinline__ int rowNode(int r) { return (0x67542310u >> (4 * r)) 
 template <int MC, bool TL, int STG = 0, bool HREC = false>
 __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg, int gp, const MatParams& mp,
                                                   const double* __restrict__ state_ref, double* __restrict__ state_temp, int64_t cstride,
-                                                  bool writeState, int* failFlag, long long* tsub = nullptr) {
+                                                  bool writeState, int* failFlag, long long* tsub = nullptr, int rowFlip16 = 0) {
 #ifdef EWB_TIMING
     long long tq0 = clock64();
 #define EWB_SUB(i) do { const long long tq1 = clock64(); if (tsub) tsub[i] += tq1 - tq0; tq0 = tq1; } while (0)
@@ -176,7 +176,7 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
             if (!(wd > 0.0)) atomicOr(failFlag, 8);  // sqrt(w detJ): inverted element
             const double sq = sqrt(wd);
             const int ks = gp >> 2, q = gp & 3;
-            double* Hq = rec + ks * RecLayoutH::KS + q;
+            double* Hq = rec + ks * RecLayoutH::KS + q;  // rowFlip16 = 16: the y bit of the row index is inverted (row-pipelined kernel, odd element rows)
             forNodes<8>([&](auto ic) {
                 constexpr int a = decltype(ic)::value;
                 constexpr int r = (0x67542310u >> (4 * a)) & 7;  // rowNode is an involution: row of node a
@@ -184,7 +184,7 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
                 shapeDeriv<8, a>(xi, eta, zeta, d);
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    Hq[2 * c * RecLayoutH::KS + 4 * r] = sq * (iJ[c * 3] * d[0] + iJ[c * 3 + 1] * d[1] + iJ[c * 3 + 2] * d[2]);
+                    Hq[2 * c * RecLayoutH::KS + 4 * r + (r < 4 ? rowFlip16 : -rowFlip16)] = sq * (iJ[c * 3] * d[0] + iJ[c * 3 + 1] * d[1] + iJ[c * 3 + 2] * d[2]);
             });
 #pragma unroll
             for (int i = 0; i < 6; ++i) rec[RecLayoutH::OFF_S + 6 * gp + i] = -sq * sg[i];

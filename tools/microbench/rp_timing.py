@@ -17,7 +17,7 @@ from edelweissfe_b200 import ElementAssembly, box_mesh  # noqa: E402
 
 what = sys.argv[1] if len(sys.argv) > 1 else "le"
 variant = os.environ.get("EWB_KERNEL", "rp4_4_4")
-npw, ntw, ngw = (int(c) for c in variant.lstrip("rps").split("_"))
+npw, ntw, ngw = (int(c) for c in variant.lstrip("rpsab").split("_"))
 n = (100, 100, 100)
 coords, conn = box_mesh(*n, lX=100.0, lY=100.0, lZ=100.0)
 if what == "vm":
