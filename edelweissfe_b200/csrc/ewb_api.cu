@@ -71,7 +71,7 @@ struct ewb_plan {
     int64_t nX = 0, nY = 0, nZ = 0;
     std::vector<int32_t> connHost;
     ewb::SweepPlan sweep;
-    int fusedVariant = 2040804;  // row-pipelined kernel, warps 10000 P + 100 T + G; 1 = first-generation sweep (EWB_KERNEL, read once at plan creation)
+    int fusedVariant = 0;  // 0 = automatic (measured best per material); 1 = first-generation sweep; else row-pipelined kernel variant (EWB_KERNEL, read once at plan creation)
 };
 
 namespace {
@@ -438,9 +438,12 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
 
     if (p->isBox && !(flags & EWB_FLAG_FORCE_GENERIC) && b->vij == nullptr) {
         if (!p->sweep.indexable()) return fail(EWB_ERR_UNSUPPORTED, "ewb_assemble: the fused BoxGen kernels index nodes with int32 (3 * nodes < 2^31); use EWB_FLAG_FORCE_GENERIC");
-        const bool v1 = (flags & EWB_FLAG_SWEEP_V1) || p->fusedVariant == 1;
+        // automatic choice (B200, round 2): linear elasticity runs the row-pipelined kernel (598 vs 551 Melem/s at 100^3); von Mises and
+        // Neo-Hooke, whose phase A is heavier than four producer warps can feed, stay on the first-generation sweep (334 vs 307, 413 vs 352)
+        const int variant = p->fusedVariant != 0 ? p->fusedVariant : (mc == ewb::MC_LE ? 3040804 : 1);
+        const bool v1 = (flags & EWB_FLAG_SWEEP_V1) || variant == 1;
         const int rc = v1 ? p->sweep.launchV1(p->elType, mc, mp, b, p->failFlag, flags, st)
-                          : ewb::launchRowPipeAny(p->sweep, p->fusedVariant, p->elType, mc, mp, b, p->failFlag, flags, st);
+                          : ewb::launchRowPipeAny(p->sweep, variant, p->elType, mc, mp, b, p->failFlag, flags, st);
         if (rc == EWB_OK) {
             countLaunch();
             return EWB_OK;

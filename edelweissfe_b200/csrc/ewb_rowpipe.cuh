@@ -670,12 +670,14 @@ int launchRowPipeVariant(SweepPlan& sp, int variant, const MatParams& mp, const 
         case 30405: return launchRowPipe<MC, TL, 7, 3, 4, 5>(sp, mp, b, failFlag, flags, st);
         case 1040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120>(sp, mp, b, failFlag, flags, st);
         case 2040404: return launchRowPipe<MC, TL, 7, 4, 4, 4, 0, 0, 0, 3>(sp, mp, b, failFlag, flags, st);
-        case 3040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 120, 104, 3>(sp, mp, b, failFlag, flags, st);
         case 4040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 152, 128, 104, 3>(sp, mp, b, failFlag, flags, st);
 #endif
         case 40404: return launchRowPipe<MC, TL, 7, 4, 4, 4>(sp, mp, b, failFlag, flags, st);
-        case 2040804:
-        default: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120, 3>(sp, mp, b, failFlag, flags, st);
+#ifdef EWB_VARIANTS
+        case 2040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120, 3>(sp, mp, b, failFlag, flags, st);
+#endif
+        case 3040804:
+        default: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 120, 104, 3>(sp, mp, b, failFlag, flags, st);
     }
 }
 

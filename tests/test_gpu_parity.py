@@ -10,6 +10,17 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 
+def _select_kernel(monkeypatch, path):
+    """The fused BoxGen kernel is chosen per material ('auto'); EWB_KERNEL (read at plan creation) forces one for every material:
+    rowpipe = row-pipelined gather sweep with y-chaining (16 warps), rowpipe444 = the same without chaining (12 warps)."""
+    if path == "rowpipe":
+        monkeypatch.setenv("EWB_KERNEL", "rpa4_8_4")
+    elif path == "rowpipe444":
+        monkeypatch.setenv("EWB_KERNEL", "rp4_4_4")
+    else:
+        monkeypatch.delenv("EWB_KERNEL", raising=False)
+
+
 def _assembly(g, box=None):
     from edelweissfe_b200 import ElementAssembly
 
@@ -17,15 +28,16 @@ def _assembly(g, box=None):
 
 
 @pytest.mark.parametrize("name", golden_names())
-@pytest.mark.parametrize("path", ["generic", "auto"])
-def test_golden(name, path):
+@pytest.mark.parametrize("path", ["generic", "auto", "rowpipe"])
+def test_golden(name, path, monkeypatch):
     import torch
 
     from edelweissfe_b200 import _lib
 
     g = load_golden(name)
     box = None
-    if path == "auto":
+    _select_kernel(monkeypatch, path)
+    if path != "generic":
         if not (bool(g["boxgen_regular"]) or True) or g["conn"].shape[1] != 8:
             pytest.skip("structured sweep is Hexa8 only")
         box = [int(v) for v in g["box"][:3]]  # BoxGen topology (coordinates may be distorted)
@@ -71,8 +83,8 @@ def test_golden(name, path):
         ("C3D20", "vonmises", [2.1e4, 0.22, 355, 1000, 200, 1400], (3, 3, 4), 5e-3),
     ],
 )
-@pytest.mark.parametrize("path", ["generic", "auto", "sweepv1"])
-def test_against_oracle_seeded(elType, material, props, n, scale, path):
+@pytest.mark.parametrize("path", ["generic", "auto", "sweepv1", "rowpipe", "rowpipe444"])
+def test_against_oracle_seeded(elType, material, props, n, scale, path, monkeypatch):
     import torch
 
     from edelweissfe_b200 import ElementAssembly, _lib, box_mesh
@@ -81,6 +93,7 @@ def test_against_oracle_seeded(elType, material, props, n, scale, path):
     nn = 20 if "20" in elType else 8
     if path != "generic" and nn != 8:
         pytest.skip("structured paths are Hexa8 only")
+    _select_kernel(monkeypatch, path)
     coords, conn = box_mesh(*n, lX=float(n[0]), lY=1.1 * n[1], lZ=0.9 * n[2], elType=elType)
     c2, conn2 = port.boxgen(*n, float(n[0]), 1.1 * n[1], 0.9 * n[2], nnodes=nn)
     assert np.array_equal(conn, conn2) and np.array_equal(coords, c2)
@@ -88,7 +101,7 @@ def test_against_oracle_seeded(elType, material, props, n, scale, path):
     if nn == 8:
         coords = coords + 0.15 * rng.uniform(-1, 1, coords.shape)
     asm = ElementAssembly(elType, conn, coords, material, props, box=n if path != "generic" else None)
-    flags = {"generic": _lib.EWB_FLAG_FORCE_GENERIC, "auto": 0, "sweepv1": _lib.EWB_FLAG_SWEEP_V1}[path]
+    flags = {"generic": _lib.EWB_FLAG_FORCE_GENERIC, "sweepv1": _lib.EWB_FLAG_SWEEP_V1}.get(path, 0)
     nGp = 27 if nn == 20 else 8
     state = np.zeros((conn.shape[0], nGp, 12 + port.MATERIAL_NSTATE[material]))
     U = np.zeros(3 * coords.shape[0])
@@ -312,8 +325,8 @@ def test_full_size_properties(workload):
 
 @pytest.mark.parametrize("n", [(1, 1, 1), (1, 1, 6), (2, 1, 1), (1, 7, 1), (6, 2, 13), (13, 6, 2), (35, 3, 3), (8, 15, 11)])
 @pytest.mark.parametrize("material", ["linearelastic", "vonmises"])
-@pytest.mark.parametrize("path", ["sweep", "sweepv1"])
-def test_sweep_edge_shapes(n, material, path):
+@pytest.mark.parametrize("path", ["sweep", "sweepv1", "rowpipe", "rowpipe444"])
+def test_sweep_edge_shapes(n, material, path, monkeypatch):
     """Degenerate and ragged boxes: tiles larger than the mesh, single element planes, several x-chunks,
     tile edges that coincide with the mesh boundary (producer/consumer and single-role kernels)."""
     import torch
@@ -322,6 +335,7 @@ def test_sweep_edge_shapes(n, material, path):
     from oracle import port
 
     props = [2.1e4, 0.22] if material == "linearelastic" else [2.1e4, 0.22, 355, 1000, 200, 1400]
+    _select_kernel(monkeypatch, path)
     coords, conn = box_mesh(*n, lX=1.0 * n[0], lY=1.2 * n[1], lZ=0.8 * n[2])
     rng = np.random.default_rng(7)
     coords = coords + 0.1 * rng.uniform(-1, 1, coords.shape)
