@@ -70,6 +70,10 @@ SYMBOLS = {
     "ewb_state_to_soa": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P]),
     "ewb_state_to_aos": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P]),
     "ewb_apply_dirichlet_k": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    "ewb_apply_dirichlet_r": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    "ewb_spmv": (C.c_int, [_P, _P, _P, _P, _P]),
+    "ewb_pcg_solve": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), _P]),
+    "ewb_surface_pressure": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_double, _P, _P]),
     "ewb_body_force": (C.c_int, [_P, _P, C.POINTER(C.c_double), _P, _P]),
     "ewb_interface_add": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "ewb_plan_set_peer": (C.c_int, [_P, _P, _P, _P]),

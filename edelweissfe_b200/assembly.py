@@ -175,9 +175,69 @@ class ElementAssembly:
         """acceptLastState for every element (element.py:373-379): stateTemp becomes stateRef."""
         self.state_ref, self.state_temp = self.state_temp, self.state_ref
 
+    def _dofs_dev(self, dofs):
+        if torch.is_tensor(dofs) and dofs.dtype == torch.int32 and dofs.device == self.device:
+            return dofs.contiguous()
+        return torch.as_tensor(np.asarray(dofs, dtype=np.int32), device=self.device).contiguous()
+
     def apply_dirichlet_k(self, dofs):
-        d = torch.as_tensor(dofs, dtype=torch.int32, device=self.device).contiguous()
+        """NIST.applyDirichletK on the device (nonlinearimplicitstatic.py:559-593, pattern kept like mk2.pyx:66-109)."""
+        d = self._dofs_dev(dofs)
         check(self.lib.ewb_apply_dirichlet_k(self.plan, _ptr(self.csr_data), _ptr(d), d.numel(), self._stream()))
+
+    def apply_dirichlet_r(self, R, dofs, values=None):
+        """NIST.applyDirichlet on a device residual (nonlinearimplicitstatic.py:595-623): R[dofs] = values (zeros when None)."""
+        d = self._dofs_dev(dofs)
+        v = None if values is None else torch.as_tensor(np.asarray(values, dtype=np.float64), device=self.device).contiguous()
+        check(self.lib.ewb_apply_dirichlet_r(_ptr(R), _ptr(d), _ptr(v), d.numel(), self._stream()))
+        return R
+
+    def spmv(self, x, y=None):
+        """y = K x with the assembled CSR values (device tensors)."""
+        if y is None:
+            y = torch.empty(self.nDof, dtype=torch.float64, device=self.device)
+        check(self.lib.ewb_spmv(self.plan, _ptr(self.csr_data), _ptr(x), _ptr(y), self._stream()))
+        return y
+
+    def pcg_solve(self, b, dirichlet_dofs=None, rel_tol=1e-10, max_iter=20000, x=None):
+        """NIST.linearSolve on the device (nonlinearimplicitstatic.py:727-751): Jacobi-PCG on the assembled matrix with the
+        Dirichlet rows treated as identity rows (x[dirichlet] = b[dirichlet]).  b, x: device tensors [nDof].
+        Returns (x, iterations, relative residual)."""
+        if x is None:
+            x = torch.empty(self.nDof, dtype=torch.float64, device=self.device)
+        d = self._dofs_dev(dirichlet_dofs if dirichlet_dofs is not None else np.zeros(0, dtype=np.int32))
+        it, rr = C.c_int(0), C.c_double(0.0)
+        check(self.lib.ewb_pcg_solve(self.plan, _ptr(self.csr_data), _ptr(b), _ptr(x), _ptr(d) if d.numel() else C.c_void_p(0), d.numel(),
+                                     float(rel_tol), int(max_iter), C.byref(it), C.byref(rr), self._stream()))
+        return x, it.value, rr.value
+
+    def pcg_solve_host(self, b, dirichlet_dofs=None, rel_tol=1e-10, max_iter=20000):
+        """Host-facing form: b [nDof] in, x [nDof] out (numpy); the matrix stays on the device."""
+        hb = self._pinned("b", self.nDof)
+        hb.numpy()[:] = b
+        bd = getattr(self, "_pcg_b", None)
+        if bd is None:
+            bd = self._pcg_b = torch.empty(self.nDof, dtype=torch.float64, device=self.device)
+            self._pcg_x = torch.empty(self.nDof, dtype=torch.float64, device=self.device)
+        bd.copy_(hb, non_blocking=True)
+        x, it, rr = self.pcg_solve(bd, dirichlet_dofs, rel_tol, max_iter, x=self._pcg_x)
+        hx = self._pinned("x", self.nDof)
+        hx.copy_(x, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return hx.numpy().copy(), it, rr
+
+    def surface_pressure(self, elems, faces, pressure, pext=None):
+        """PExt += pressure load on the (element index, Abaqus face id) pairs (computeDistributedLoads, :460-508)."""
+        if pext is None:
+            pext = torch.zeros(self.nDof, dtype=torch.float64, device=self.device)
+        e = np.ascontiguousarray(np.asarray(elems, dtype=np.int32))
+        f = np.ascontiguousarray(np.asarray(faces, dtype=np.int32))
+        check(self.lib.ewb_surface_pressure(self.plan, _ptr(self.coords), e.size, e.ctypes.data_as(C.c_void_p), f.ctypes.data_as(C.c_void_p),
+                                            float(pressure), _ptr(pext), self._stream()))
+        return pext
+
+    def surface_pressure_host(self, elems, faces, pressure):
+        return self.surface_pressure(elems, faces, pressure).cpu().numpy()
 
     # ---- state layout --------------------------------------------------------------------------
     def state_aos(self, which="temp"):
@@ -201,30 +261,60 @@ class ElementAssembly:
             setattr(self, "_pin_" + name, buf)
         return buf
 
-    def compute_host(self, U, dU, stateRef_aos, stateTemp_aos, time=(0.0, 0.0), dT=0.0, flags=0):
-        """computeElements with HOST arrays: U, dU [nDof], stateRef [nEl,nGp,nState] in; returns (P, F) and
-        fills stateTemp_aos in place.  K stays on the device until csr_data_host().  Raises CutbackRequest."""
+    def compute_host(self, U, dU, stateRef_aos=None, stateTemp_aos=None, time=(0.0, 0.0), dT=0.0, flags=0):
+        """computeElements with HOST arrays (what the solver plugin calls): U, dU [nDof] in, (P, F) out; K stays on the device
+        (csr_data_host() / the device solver consume it).  Raises CutbackRequest.
+
+        Gauss-point state is DEVICE RESIDENT by default: the pass reads state_ref and writes state_temp on the device, and the
+        caller commits with accept_last_state() / reads back with download_state_temp() when an increment is accepted — per Newton
+        iteration only 2 + 2 dof vectors cross PCIe.  Passing stateRef_aos / stateTemp_aos ([nEl, nGp, nState], the reference's
+        per-element layout) restores the stateless form: stateRef is uploaded before and stateTemp downloaded after the pass."""
         hU, hdU = self._pinned("U", self.nDof), self._pinned("dU", self.nDof)
         hU.numpy()[:] = U
         hdU.numpy()[:] = dU
-        hS = self._pinned("S", self.nEl * self.nGp * self.nState)
-        hS.numpy()[:] = np.asarray(stateRef_aos).reshape(-1)
         self.U.copy_(hU, non_blocking=True)
         self.dU.copy_(hdU, non_blocking=True)
-        scratch = getattr(self, "_aos_scratch", None)
-        if scratch is None:
-            scratch = self._aos_scratch = torch.empty(self.nEl * self.nGp * self.nState, dtype=torch.float64, device=self.device)
-        scratch.copy_(hS, non_blocking=True)
-        check(self.lib.ewb_state_to_soa(_ptr(scratch), _ptr(self.state_ref), self.nEl, self.nGp, self.nState, self._stream()))
+        if stateRef_aos is not None:
+            self.upload_state_ref(stateRef_aos)
         self.assemble(flags, time=time, dT=dT)
-        check(self.lib.ewb_state_to_aos(_ptr(self.state_temp), _ptr(scratch), self.nEl, self.nGp, self.nState, self._stream()))
         hP, hF = self._pinned("P", self.nDof), self._pinned("F", self.nDof)
         hP.copy_(self.P, non_blocking=True)
         hF.copy_(self.F, non_blocking=True)
-        hS.copy_(scratch, non_blocking=True)
+        if stateTemp_aos is not None:
+            self.download_state_temp(stateTemp_aos, sync=False)
         self.poll()
-        np.asarray(stateTemp_aos).reshape(-1)[:] = hS.numpy()
+        if stateTemp_aos is not None:
+            np.asarray(stateTemp_aos).reshape(-1)[:] = self._pinned("S", self.nEl * self.nGp * self.nState).numpy()
         return hP.numpy().copy(), hF.numpy().copy()
+
+    def _aos_device_scratch(self):
+        scratch = getattr(self, "_aos_scratch", None)
+        if scratch is None:
+            scratch = self._aos_scratch = torch.empty(self.nEl * self.nGp * self.nState, dtype=torch.float64, device=self.device)
+        return scratch
+
+    def upload_state_ref(self, stateRef_aos):
+        """Host [nEl, nGp, nState] (the elements' _stateVarsRef, element.py:225-236) -> device state_ref (SoA)."""
+        hS = self._pinned("S", self.nEl * self.nGp * self.nState)
+        hS.numpy()[:] = np.asarray(stateRef_aos).reshape(-1)
+        scratch = self._aos_device_scratch()
+        scratch.copy_(hS, non_blocking=True)
+        check(self.lib.ewb_state_to_soa(_ptr(scratch), _ptr(self.state_ref), self.nEl, self.nGp, self.nState, self._stream()))
+
+    def download_state_temp(self, out=None, sync=True):
+        """Device state_temp (SoA) -> host [nEl, nGp, nState]; `out` is filled in place when given."""
+        hS = self._pinned("S", self.nEl * self.nGp * self.nState)
+        scratch = self._aos_device_scratch()
+        check(self.lib.ewb_state_to_aos(_ptr(self.state_temp), _ptr(scratch), self.nEl, self.nGp, self.nState, self._stream()))
+        hS.copy_(scratch, non_blocking=True)
+        if not sync:
+            return None
+        torch.cuda.current_stream(self.device).synchronize()
+        res = hS.numpy().reshape(self.nEl, self.nGp, self.nState)
+        if out is not None:
+            np.asarray(out).reshape(self.nEl, self.nGp, self.nState)[...] = res
+            return out
+        return res.copy()
 
     def csr_pattern_host(self):
         indptr, indices = self.csr_pattern()

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,6 +15,7 @@
 #include "ewb_generic.cuh"
 #include "ewb_sweep.cuh"
 #include "ewb_rowpipe.cuh"
+#include "ewb_solver.cuh"
 
 namespace {
 
@@ -66,6 +68,12 @@ struct ewb_plan {
     int* failHost = nullptr;     // pinned mirror
     double* peScratch = nullptr; // [nEl][3nn] per-element residual (generic path)
     double* vijScratch = nullptr;
+    // device consumer (ewb_pcg_solve): r, z, p, q, Minv, mask [nDof] each; partial sums; scalars; pinned mirror of the scalars
+    double* pcgWork = nullptr;
+    double* pcgPartial = nullptr;
+    double* pcgScal = nullptr;
+    double* pcgScalHost = nullptr;
+    int64_t pcgBlocks = 0;
     // structured (BoxGen) description
     bool isBox = false;
     int64_t nX = 0, nY = 0, nZ = 0;
@@ -218,9 +226,15 @@ int ewb_plan_create(ewb_plan** out, int el_type, int64_t n_el, int64_t n_node, c
         ewb_plan_destroy(p);
         return rc;
     }
-    CUDA_TRY(cudaMalloc((void**)&p->failFlag, sizeof(int)));
-    CUDA_TRY(cudaMemset(p->failFlag, 0, sizeof(int)));
-    CUDA_TRY(cudaMallocHost((void**)&p->failHost, sizeof(int)));
+    {
+        cudaError_t e = cudaMalloc((void**)&p->failFlag, sizeof(int));
+        if (e == cudaSuccess) e = cudaMemset(p->failFlag, 0, sizeof(int));
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&p->failHost, sizeof(int));
+        if (e != cudaSuccess) {
+            ewb_plan_destroy(p);
+            return fail(EWB_ERR_CUDA, std::string("ewb_plan_create: ") + cudaGetErrorString(e));
+        }
+    }
     *p->failHost = 0;
     *out = p;
     return EWB_OK;
@@ -231,6 +245,8 @@ void ewb_plan_destroy(ewb_plan* p) {
     cudaSetDevice(p->device);
     cudaFree(p->conn); cudaFree(p->adjPtr); cudaFree(p->adj); cudaFree(p->incPtr); cudaFree(p->inc);
     cudaFree(p->failFlag); cudaFree(p->peScratch); cudaFree(p->vijScratch); cudaFree(p->gatherOrder); cudaFree(p->gatherSlots);
+    cudaFree(p->pcgWork); cudaFree(p->pcgPartial); cudaFree(p->pcgScal);
+    if (p->pcgScalHost) cudaFreeHost(p->pcgScalHost);
     if (p->failHost) cudaFreeHost(p->failHost);
     p->sweep.release();
     delete p;
@@ -636,6 +652,139 @@ int ewb_apply_dirichlet_k(const ewb_plan* p, double* data, const int32_t* dofs_d
     CUDA_TRY(cudaSetDevice(p->device));
     dirichletKernel<<<(unsigned)n, 96, 0, (cudaStream_t)stream>>>(nullptr, p->adjPtr, p->adj, data, dofs_dev, n);
     LAUNCH_CHECK();
+    return EWB_OK;
+}
+
+
+int ewb_apply_dirichlet_r(double* r_dev, const int32_t* dofs_dev, const double* values_dev, int64_t n, void* stream) {
+    if (!r_dev || (!dofs_dev && n > 0)) return fail(EWB_ERR_ARG, "ewb_apply_dirichlet_r: bad arguments");
+    if (n == 0) return EWB_OK;
+    ewb::dirichletRKernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(r_dev, dofs_dev, values_dev, n);
+    LAUNCH_CHECK();
+    return EWB_OK;
+}
+
+int ewb_spmv(const ewb_plan* p, const double* csr_data_dev, const double* x_dev, double* y_dev, void* stream) {
+    if (!p || !csr_data_dev || !x_dev || !y_dev) return fail(EWB_ERR_ARG, "ewb_spmv: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    ewb::spmvNodeKernel<false, false><<<(unsigned)((p->nNode + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p->nNode, p->adjPtr, p->adj, csr_data_dev, x_dev, y_dev,
+                                                                                                      nullptr, nullptr, nullptr);
+    LAUNCH_CHECK();
+    return EWB_OK;
+}
+
+int ewb_pcg_solve(ewb_plan* p, const double* A, const double* b, double* x, const int32_t* dirichlet_dofs_dev, int64_t n_dirichlet, double rel_tol,
+                  int max_iter, int* iters_out, double* relres_out, void* stream) {
+    if (!p || !A || !b || !x || (n_dirichlet > 0 && !dirichlet_dofs_dev) || max_iter < 0) return fail(EWB_ERR_ARG, "ewb_pcg_solve: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nDof = 3 * p->nNode;
+    const int64_t nbV = (nDof + 255) / 256, nbS = (p->nNode + 7) / 8;
+    const int64_t stride = std::max(nbV, nbS);
+    if (!p->pcgWork) {
+        CUDA_TRY(cudaMalloc((void**)&p->pcgWork, (size_t)6 * nDof * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void**)&p->pcgPartial, (size_t)2 * stride * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void**)&p->pcgScal, 8 * sizeof(double)));
+        CUDA_TRY(cudaMallocHost((void**)&p->pcgScalHost, 8 * sizeof(double)));
+        p->pcgBlocks = stride;
+    }
+    double *r = p->pcgWork, *z = r + nDof, *pp = z + nDof, *q = pp + nDof, *minv = q + nDof, *mask = minv + nDof;
+    double* partial = p->pcgPartial;
+    double* scal = p->pcgScal;
+    const unsigned gV = (unsigned)nbV, gS = (unsigned)nbS;
+    CUDA_TRY(cudaMemsetAsync(scal, 0, 8 * sizeof(double), st));
+    ewb::fillKernel<<<gV, 256, 0, st>>>(mask, nDof, 1.0);
+    LAUNCH_CHECK();
+    if (n_dirichlet > 0) {
+        ewb::maskKernel<<<(unsigned)((n_dirichlet + 255) / 256), 256, 0, st>>>(mask, nDof, dirichlet_dofs_dev, n_dirichlet);
+        LAUNCH_CHECK();
+    }
+    ewb::pcgSetupKernel<<<gV, 256, 0, st>>>(nDof, p->adjPtr, p->adj, A, b, mask, minv, x);
+    LAUNCH_CHECK();
+    // q = A x0;  r = m (b - q), z = Minv r, p = z
+    ewb::spmvNodeKernel<false, false><<<gS, 256, 0, st>>>(p->nNode, p->adjPtr, p->adj, A, x, q, nullptr, nullptr, nullptr);
+    LAUNCH_CHECK();
+    ewb::pcgInitKernel<<<gV, 256, 0, st>>>(nDof, b, q, mask, minv, r, z, pp, partial, stride);
+    LAUNCH_CHECK();
+    ewb::reduceKernel<<<1, 1024, 0, st>>>(partial, nbV, scal + 2, 2, stride);  // rzNew, rr
+    LAUNCH_CHECK();
+    ewb::pcgShiftKernel<<<1, 1, 0, st>>>(scal, 1);  // rz = rzNew, rr0 = rr
+    LAUNCH_CHECK();
+    int it = 0;
+    double relres = 0.0;
+    const int CHECK = 16;
+    while (true) {
+        if (it % CHECK == 0 || it >= max_iter) {
+            CUDA_TRY(cudaMemcpyAsync(p->pcgScalHost, scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            const double rr = p->pcgScalHost[3], rr0 = p->pcgScalHost[4];
+            relres = rr0 > 0.0 ? std::sqrt(rr / rr0) : 0.0;
+            if (!(rr == rr)) return fail(EWB_ERR_CUDA, "ewb_pcg_solve: NaN residual (singular or indefinite matrix)");
+            if (relres <= rel_tol || it >= max_iter) break;
+        }
+        ewb::spmvNodeKernel<true, true><<<gS, 256, 0, st>>>(p->nNode, p->adjPtr, p->adj, A, pp, q, mask, pp, partial);
+        LAUNCH_CHECK();
+        ewb::reduceKernel<<<1, 1024, 0, st>>>(partial, nbS, scal + 1, 1, stride);  // pq
+        LAUNCH_CHECK();
+        ewb::pcgUpdateKernel<<<gV, 256, 0, st>>>(nDof, scal, pp, q, minv, x, r, z, partial, stride);
+        LAUNCH_CHECK();
+        ewb::reduceKernel<<<1, 1024, 0, st>>>(partial, nbV, scal + 2, 2, stride);  // rzNew, rr
+        LAUNCH_CHECK();
+        ewb::pcgDirectionKernel<<<gV, 256, 0, st>>>(nDof, scal, z, pp);
+        LAUNCH_CHECK();
+        ewb::pcgShiftKernel<<<1, 1, 0, st>>>(scal, 0);
+        LAUNCH_CHECK();
+        ++it;
+    }
+    if (iters_out) *iters_out = it;
+    if (relres_out) *relres_out = relres;
+    return EWB_OK;
+}
+
+int ewb_surface_pressure(ewb_plan* p, const double* coords_dev, int64_t n_faces, const int32_t* elem_host, const int32_t* face_host, double pressure,
+                         double* pext_dev, void* stream) {
+    if (!p || !coords_dev || !pext_dev || n_faces < 0 || (n_faces > 0 && (!elem_host || !face_host))) return fail(EWB_ERR_ARG, "ewb_surface_pressure: bad arguments");
+    if (p->nn != 8) return fail(EWB_ERR_UNSUPPORTED, "ewb_surface_pressure: 4-node faces of 8-node hexahedra only");
+    if (n_faces == 0) return EWB_OK;
+    CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    static const int faceNodes[6][4] = {{0, 3, 2, 1}, {4, 5, 6, 7}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}};
+    // loaded nodes and their (face, local node) incidence in ascending order: fixed summation order
+    std::vector<std::pair<int32_t, int32_t>> pairs;  // (node, 4 f + a)
+    pairs.reserve((size_t)4 * n_faces);
+    for (int64_t f = 0; f < n_faces; ++f) {
+        if (elem_host[f] < 0 || elem_host[f] >= p->nEl || face_host[f] < 1 || face_host[f] > 6) return fail(EWB_ERR_ARG, "ewb_surface_pressure: element / face id out of range");
+        for (int a = 0; a < 4; ++a) pairs.emplace_back(p->connHost[(size_t)elem_host[f] * 8 + faceNodes[face_host[f] - 1][a]], (int32_t)(4 * f + a));
+    }
+    std::sort(pairs.begin(), pairs.end());
+    std::vector<int32_t> nodes, inc(pairs.size());
+    std::vector<int64_t> incPtr;
+    for (size_t k = 0; k < pairs.size(); ++k) {
+        if (k == 0 || pairs[k].first != pairs[k - 1].first) { nodes.push_back(pairs[k].first); incPtr.push_back((int64_t)k); }
+        inc[k] = pairs[k].second;
+    }
+    incPtr.push_back((int64_t)pairs.size());
+    int32_t *dElem = nullptr, *dFace = nullptr, *dNodes = nullptr, *dInc = nullptr;
+    int64_t* dIncPtr = nullptr;
+    double* scratch = nullptr;
+    std::vector<int32_t> eh(elem_host, elem_host + n_faces), fh(face_host, face_host + n_faces);
+    int rc = EWB_OK;
+    if ((rc = upload(&dElem, eh)) || (rc = upload(&dFace, fh)) || (rc = upload(&dNodes, nodes)) || (rc = upload(&dInc, inc)) || (rc = upload(&dIncPtr, incPtr))) {
+        cudaFree(dElem); cudaFree(dFace); cudaFree(dNodes); cudaFree(dInc); cudaFree(dIncPtr);
+        return rc;
+    }
+    cudaError_t e = cudaMalloc((void**)&scratch, (size_t)12 * n_faces * sizeof(double));
+    if (e == cudaSuccess) {
+        ewb::facePressureKernel<<<(unsigned)((n_faces + 127) / 128), 128, 0, st>>>(n_faces, dElem, dFace, p->conn, coords_dev, pressure, scratch);
+        countLaunch();
+        const int64_t nL = (int64_t)nodes.size();
+        ewb::faceGatherKernel<<<(unsigned)((3 * nL + 127) / 128), 128, 0, st>>>(nL, dNodes, dIncPtr, dInc, scratch, pext_dev);
+        countLaunch();
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the temporary tables are freed below
+    }
+    cudaFree(dElem); cudaFree(dFace); cudaFree(dNodes); cudaFree(dInc); cudaFree(dIncPtr); cudaFree(scratch);
+    if (e != cudaSuccess) return fail(EWB_ERR_CUDA, std::string("ewb_surface_pressure: ") + cudaGetErrorString(e));
     return EWB_OK;
 }
 

@@ -17,9 +17,16 @@ Overridden members of NIST (solvers/nonlinearimplicitstatic.py):
 The element contributions never pass through the VIJ triple: K (VIJ) keeps only what constraints write
 into it afterwards (:889-896); assembleStiffnessCSR merges both into the reference's CSR pattern.
 
-Gauss-point state stays visible to the reference: every element's `_stateVarsRef` / `_stateVarsTemp`
-(element.py:225-236) are re-bound to views of two contiguous host arrays, so `acceptLastState`
-(element.py:373-379), field outputs and `getResultArray` work unchanged.
+Gauss-point state is device resident during the Newton iterations.  The elements' own `_stateVarsRef` /
+`_stateVarsTemp` arrays (element.py:225-236) are never re-bound — field outputs cache raw pointers into them
+(utils/elementresultcollector.pyx:83-97): when an increment is accepted (`model.advanceToTime`, models/femodel.py:245-258)
+the plugin first downloads the converged state into every element's `_stateVarsTemp` IN PLACE and swaps the device
+buffers, then the reference's own `acceptLastState` (element.py:373-379) copies it into `_stateVarsRef` as always.
+
+With `*solver, solver=NISTB200, ..., b200solver=pcg` the matrix never leaves the device either: `assembleStiffnessCSR`
+returns a device handle, `applyDirichletK` (:559-593) zeroes the rows on the device and `linearSolve` (:727-751) runs
+the hand-written Jacobi-PCG; per iteration only dof-sized vectors cross PCIe.  The default (`b200solver=host`) hands a
+scipy CSR matrix to whatever `linsolver=` names, like the reference.
 
 This module needs the reference package to be importable; it is not used by bench.py or the GPU tests
 (the GPU box has no reference tree).  Host-side logic is tested on CPU in tests/test_plugin_reference.py.
@@ -92,17 +99,16 @@ class ElementSetExtraction:
         self.coords = coords
         self.nState = els[0]._stateVarsRef.shape[1]
         self.nInt = nInt
-        # one contiguous host image of the Gauss-point state; the elements keep working on views of it
-        self.stateRef = np.array([np.asarray(e._stateVarsRef) for e in els])
-        self.stateTemp = np.array([np.asarray(e._stateVarsTemp) for e in els]) if np.shape(els[0]._stateVarsTemp) == np.shape(els[0]._stateVarsRef) else self.stateRef.copy()
-        for k, e in enumerate(els):
-            e._stateVarsRef = self.stateRef[k]
-            e._stateVarsTemp = self.stateTemp[k]
-            for i in range(nInt):
-                sv = e._stateVars[i]
-                sv["stress"] = self.stateRef[k, i, 0:6]
-                sv["strain"] = self.stateRef[k, i, 6:12]
-                sv["materialstate"] = self.stateRef[k, i, 12:]
+
+    def gather_state_ref(self):
+        """Contiguous [nEl, nInt, nState] copy of the elements' accepted state (element.py:225-236)."""
+        return np.array([np.asarray(e._stateVarsRef) for e in self.elements])
+
+    def scatter_state_temp(self, stateTemp):
+        """Write the converged state into every element's OWN _stateVarsTemp array, in place (pointers held by field
+        outputs stay valid); the reference's acceptLastState then copies it into _stateVarsRef (element.py:373-379)."""
+        for e, st in zip(self.elements, stateTemp):
+            e._stateVarsTemp[...] = st
 
     def detect_box(self):
         """(nX, nY, nZ) if the connectivity is BoxGen-ordered (generators/boxgen.py:168-185), else None."""
@@ -131,27 +137,61 @@ def make_solver_class(backend_factory=default_backend):
     from edelweissfe.solvers.nonlinearimplicitstatic import NIST
     from edelweissfe.utils.exceptions import CutbackRequest
 
+    class DeviceCSR:
+        """What assembleStiffnessCSR returns with b200solver=pcg: the assembled matrix as a device handle (no values on the host)."""
+
+        def __init__(self, asm):
+            self.asm = asm
+            self.dirichlet = None
+            self.shape = (asm.nDof, asm.nDof)
+
+        def to_scipy(self):
+            import scipy.sparse as sp
+
+            indptr, indices = self.asm.csr_pattern_host()
+            return sp.csr_matrix((self.asm.csr_data_host().copy(), indices, indptr), shape=self.shape)
+
     class NISTB200(NIST):
         identification = "NISTB200Solver"
+        # b200solver: "host" = scipy CSR for the reference's linsolver (default), "pcg" = matrix stays on the device (Jacobi-PCG)
+        NISTOptions = dict(NIST.NISTOptions, b200solver="host", b200pcgtol=1e-12, b200pcgmaxiter=100000)
 
         def _b200_setup(self, elements):
             self._b200_dm = self.theDofManager
             ex = ElementSetExtraction(elements, self.theDofManager)
             self._b200_ex = ex
             self._b200_asm = backend_factory(ex.elType, ex.conn, ex.coords, ex.material, ex.props, box=ex.detect_box())
+            self._b200_asm.upload_state_ref(ex.gather_state_ref())  # the device copy is authoritative until the step ends
             self._b200_map = None
+            self._b200_index = {id(e): k for k, e in enumerate(ex.elements)}
             self.journal.message(
                 f"B200 element loop: {len(ex.elements)} x {ex.elType} / {ex.material}, "
                 f"{'fused BoxGen sweep' if ex.detect_box() else 'generic two-phase'} path", self.identification, 0)
+
+        def solveStep(self, step, model, fieldOutputController, outputmanagers):
+            """NIST.solveStep (:110-332) with the state commit hooked into model.advanceToTime (:296, models/femodel.py:245-258)."""
+            original = model.advanceToTime
+
+            def advanceToTime(time):
+                asm = getattr(self, "_b200_asm", None)
+                if asm is not None and getattr(self, "_b200_dm", None) is self.theDofManager:
+                    self._b200_ex.scatter_state_temp(asm.download_state_temp())  # in place: field-output pointers stay valid
+                    asm.accept_last_state()
+                return original(time)
+
+            model.advanceToTime = advanceToTime
+            try:
+                return super().solveStep(step, model, fieldOutputController, outputmanagers)
+            finally:
+                del model.advanceToTime
 
         def computeElements(self, elements, U_np, dU, P, K, F, timeStep):
             tic = _time.time()
             if getattr(self, "_b200_dm", None) is not self.theDofManager:
                 self._b200_setup(elements)
-            ex, asm = self._b200_ex, self._b200_asm
+            asm = self._b200_asm
             try:
-                Pel, Fel = asm.compute_host(np.asarray(U_np), np.asarray(dU), ex.stateRef, ex.stateTemp,
-                                            time=(timeStep.stepTime, timeStep.totalTime), dT=timeStep.timeIncrement)
+                Pel, Fel = asm.compute_host(np.asarray(U_np), np.asarray(dU), time=(timeStep.stepTime, timeStep.totalTime), dT=timeStep.timeIncrement)
             except Exception as e:  # device-side material failure -> the reference's cut-back request
                 if type(e).__name__ == "CutbackRequest":
                     raise CutbackRequest(str(e), e.cutbackSize)
@@ -177,16 +217,69 @@ def make_solver_class(backend_factory=default_backend):
                 return super().computeBodyForces(rest, U_np, PExt, K, timeStep)
             return PExt, K
 
+        def computeDistributedLoads(self, distributedLoads, U_np, PExt, K, timeStep):
+            """`type=pressure` on faces of 8-node hexahedra runs on the device (:460-508; the reference's Python element raises for
+            every distributed load, element.py:255-288, so this is what makes BASELINE config 1 runnable with provider=edelweiss);
+            anything else goes to the reference loop."""
+            tic = _time.time()
+            rest = []
+            for dLoad in distributedLoads:
+                asm = getattr(self, "_b200_asm", None)
+                idx = getattr(self, "_b200_index", {})
+                ok = asm is not None and hasattr(asm, "surface_pressure_host") and dLoad.loadType == "pressure" and self._b200_ex.conn.shape[1] == 8 \
+                    and all(id(el) in idx for els in dLoad.surface.values() for el in els)
+                if not ok:
+                    rest.append(dLoad)
+                    continue
+                elems = [idx[id(el)] for els in dLoad.surface.values() for el in els]
+                faces = [int(faceID) for faceID, els in dLoad.surface.items() for _ in els]
+                load = np.atleast_1d(np.asarray(dLoad.getCurrentLoad(timeStep), dtype=float))
+                PExt += asm.surface_pressure_host(elems, faces, float(load[0]))
+            self.computationTimes["distributed loads"] += _time.time() - tic
+            if rest:
+                return super().computeDistributedLoads(rest, U_np, PExt, K, timeStep)
+            return PExt, K
+
+        def _b200_device_solver(self):
+            return str(self.options.get("b200solver", "host")).lower() == "pcg" and hasattr(self._b200_asm, "pcg_solve_host")
+
         def assembleStiffnessCSR(self, K):
             tic = _time.time()
-            KCsr = self.csrGenerator.updateCSR(K)  # whatever constraints wrote into the VIJ (elements left it zero)
             asm = self._b200_asm
+            if self._b200_device_solver():
+                if np.any(np.asarray(K)):
+                    raise NotImplementedError("b200solver=pcg: constraints that write into the system matrix need b200solver=host")
+                self.computationTimes["CSR generation"] += _time.time() - tic
+                return DeviceCSR(asm)
+            KCsr = self.csrGenerator.updateCSR(K)  # whatever constraints wrote into the VIJ (elements left it zero)
             if self._b200_map is None:
                 indptr, indices = asm.csr_pattern_host()
                 self._b200_map = _pattern_map(indptr, indices, KCsr.indptr, KCsr.indices)
             KCsr.data[self._b200_map] += asm.csr_data_host()
             self.computationTimes["CSR generation"] += _time.time() - tic
             return KCsr
+
+        def applyDirichletK(self, K, dirichlets):
+            if not isinstance(K, DeviceCSR):
+                return super().applyDirichletK(K, dirichlets)
+            tic = _time.time()
+            if dirichlets:
+                K.dirichlet = np.concatenate([np.asarray(self.findDirichletIndices(d)).ravel() for d in dirichlets]).astype(np.int32)
+                K.asm.apply_dirichlet_k(K.dirichlet)  # rows zeroed, 1 on the diagonal, on the device (:559-593)
+            self.computationTimes["dirichlet K"] += _time.time() - tic
+            return K
+
+        def linearSolve(self, A, b):
+            if not isinstance(A, DeviceCSR):
+                return super().linearSolve(A, b)
+            from edelweissfe.utils.exceptions import DivergingSolution
+
+            tic = _time.time()
+            ddU, iters, relres = A.asm.pcg_solve_host(np.asarray(b), A.dirichlet, float(self.options["b200pcgtol"]), int(self.options["b200pcgmaxiter"]))
+            self.computationTimes["linear solve"] += _time.time() - tic
+            if np.isnan(ddU).any() or relres > 1e3 * float(self.options["b200pcgtol"]):
+                raise DivergingSolution("device PCG did not converge (%d iterations, relative residual %.2e)" % (iters, relres))
+            return ddU
 
     return NISTB200
 

@@ -134,6 +134,29 @@ int ewb_state_to_aos(const double* soa_dev, double* aos_dev, int64_t n_el, int n
  * zero the CSR rows of the given dofs and put 1 on their diagonal (pattern unchanged). */
 int ewb_apply_dirichlet_k(const ewb_plan* plan, double* csr_data_dev, const int32_t* dofs_dev, int64_t n, void* stream);
 
+/* ---- device-side consumers of the assembled system --------------------------------------
+ * NIST.applyDirichlet on the residual (solvers/nonlinearimplicitstatic.py:595-623): R[dofs[k]] = values[k];
+ * values_dev == NULL writes zeros (the later iterations' R[dirichlet] = 0, :432-433). */
+int ewb_apply_dirichlet_r(double* r_dev, const int32_t* dofs_dev, const double* values_dev, int64_t n, void* stream);
+/* y = K x on the plan's CSR pattern (FP64, one warp per node).  What a device linear solver builds on; also lets tests
+ * check K x against the reference's scipy matrix (csr_matrix.dot, used by linearSolve's callers). */
+int ewb_spmv(const ewb_plan* plan, const double* csr_data_dev, const double* x_dev, double* y_dev, void* stream);
+/* NIST.linearSolve (solvers/nonlinearimplicitstatic.py:727-751) for the system after applyDirichletK (:559-593), on the
+ * device: Jacobi-preconditioned conjugate gradients on the free dofs, x[dirichlet] = b[dirichlet] (the prescribed rows are
+ * identity rows).  csr_data_dev is NOT modified (rows of the Dirichlet dofs are skipped through the mask, so calling
+ * ewb_apply_dirichlet_k first is allowed but not required).  Stops at |r| <= rel_tol |r0| or max_iter; synchronises `stream`.
+ * Reductions have a fixed order: the result is bitwise reproducible. */
+int ewb_pcg_solve(ewb_plan* plan, const double* csr_data_dev, const double* b_dev, double* x_dev, const int32_t* dirichlet_dofs_dev,
+                  int64_t n_dirichlet, double rel_tol, int max_iter, int* iters_out, double* relres_out, void* stream);
+
+/* ---- distributed surface load (NIST.computeDistributedLoads, solvers/nonlinearimplicitstatic.py:460-508) for
+ * `type=pressure` on 4-node faces of 8-node hexahedra: PExt += -p int N n dA over the listed (element, Abaqus face id 1..6)
+ * pairs, dead load on the reference geometry (what BASELINE config 1, testfiles/LinearElasticIsotropic/test.inp, applies
+ * through the Marmot element; the reference's own Python element raises for distributed loads, element.py:255-288).
+ * elem_host / face_host: HOST int32 arrays (surface definitions are set-up data).  Synchronises `stream`. */
+int ewb_surface_pressure(ewb_plan* plan, const double* coords_dev, int64_t n_faces, const int32_t* elem_host, const int32_t* face_host,
+                         double pressure, double* pext_dev, void* stream);
+
 /* ---- body force element loop: NIST.computeBodyForces (solvers/nonlinearimplicitstatic.py:516-557) with
  * computeBodyForce of every element of the plan (elements/displacementelement/element.py:348-371, same in the TL element):
  * PExt[el] += sum_gp outer(N[gp], load) detJ w.  The reference's N operator node ordering (xi/eta swapped relative to the

@@ -514,6 +514,31 @@ def body_force(eltype, coords, conn, load):
     return np.bincount(dofs.reshape(-1), weights=Pe.reshape(-1), minlength=3 * coords.shape[0]), Pe
 
 
+# Abaqus face numbering of the 8-node hexahedron (faces 1..6), local nodes ordered so that the right-hand rule gives the OUTWARD normal.
+HEX8_FACES = np.array([[0, 3, 2, 1], [4, 5, 6, 7], [0, 1, 5, 4], [1, 2, 6, 5], [2, 3, 7, 6], [3, 0, 4, 7]])
+
+
+def surface_pressure(coords, conn, elems, faces, pressure):
+    """PExt of a pressure load (positive = pushing into the element) on (element, face id 1..6) pairs of 8-node hexahedra:
+    f_a = -p int N_a n dA with the bilinear face interpolation and 2x2 Gauss points; dead load on the reference geometry.
+    The algorithm is the Marmot displacement element's (un-vendored third-party code, SURVEY §8c: pinned only by
+    testfiles/LinearElasticIsotropic/U.ref); called from solvers/nonlinearimplicitstatic.py:460-508."""
+    P = np.zeros(3 * coords.shape[0])
+    g = 1.0 / np.sqrt(3.0)
+    rs = np.array([[-1.0, -1.0], [1.0, -1.0], [1.0, 1.0], [-1.0, 1.0]])
+    for e, f in zip(np.asarray(elems), np.asarray(faces)):
+        nodes = conn[e][HEX8_FACES[f - 1]]
+        X = coords[nodes]
+        for r, s_ in g * rs:
+            N = 0.25 * (1 + rs[:, 0] * r) * (1 + rs[:, 1] * s_)
+            dr = 0.25 * rs[:, 0] * (1 + rs[:, 1] * s_)
+            ds = 0.25 * rs[:, 1] * (1 + rs[:, 0] * r)
+            nA = np.cross(dr @ X, ds @ X)
+            for a in range(4):
+                P[3 * nodes[a] : 3 * nodes[a] + 3] -= pressure * N[a] * nA
+    return P
+
+
 def compute_elements(eltype, material, props, coords, conn, U, dU, stateRef, chunk=4096):
     """Batched element evaluation in element order; returns Ke, Pe, stateTemp, failed."""
     eltype = eltype.upper()
