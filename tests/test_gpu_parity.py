@@ -373,3 +373,88 @@ def test_body_force_golden(name):
     pext = torch.ones(asm.nDof, dtype=torch.float64, device=asm.device)
     asm.body_force(g["bodyforce_load"], pext)
     assert relerr(pext.cpu().numpy() - 1.0, g["bodyforce_PExt"]) < 1e-11
+
+
+def _assembled_box(n=(6, 5, 4), material="linearelastic", props=(2.1e4, 0.22)):
+    import torch
+
+    from edelweissfe_b200 import ElementAssembly, box_mesh
+
+    coords, conn = box_mesh(*n, lX=float(n[0]), lY=float(n[1]), lZ=float(n[2]))
+    rng = np.random.default_rng(3)
+    coords = coords + 0.1 * rng.uniform(-1, 1, coords.shape)
+    asm = ElementAssembly("C3D8", conn, coords, material, list(props), box=n)
+    dU = 1e-3 * rng.standard_normal(asm.nDof)
+    asm.U.copy_(torch.as_tensor(dU))
+    asm.dU.copy_(torch.as_tensor(dU))
+    asm.assemble()
+    asm.poll()
+    return asm, coords, conn, rng
+
+
+def test_spmv_matches_scipy():
+    import torch
+
+    asm, coords, conn, rng = _assembled_box()
+    K = asm.to_scipy()
+    x = rng.standard_normal(asm.nDof)
+    y = asm.spmv(torch.as_tensor(x).to(asm.device)).cpu().numpy()
+    assert relerr(y, K @ x) < 1e-13
+
+
+def test_dirichlet_r_and_pcg_solve():
+    """Device consumer of the matrix: applyDirichlet on R (nonlinearimplicitstatic.py:595-623), applyDirichletK (:559-593) and the
+    linear solve (:727-751) against the reference's own sequence on the host (scipy spsolve = the reference's superlu option)."""
+    import scipy.sparse.linalg as spla
+    import torch
+
+    n = (6, 5, 4)
+    asm, coords, conn, rng = _assembled_box(n)
+    K = asm.to_scipy().tolil()
+    fixed = np.where(coords[:, 0] < 0.5)[0]  # the x = 0 face
+    dofs = np.concatenate([3 * fixed, 3 * fixed + 1, 3 * fixed + 2]).astype(np.int32)
+    delta = 1e-3 * rng.standard_normal(dofs.size)
+    R = rng.standard_normal(asm.nDof)
+    # reference sequence on the host
+    Rh = R.copy()
+    Rh[dofs] = delta
+    Kh = K.copy()
+    for d in dofs:
+        Kh[d, :] = 0.0
+        Kh[d, d] = 1.0
+    xh = spla.spsolve(Kh.tocsc(), Rh)
+    # device
+    Rd = torch.as_tensor(R).to(asm.device)
+    asm.apply_dirichlet_r(Rd, dofs, delta)
+    assert np.array_equal(Rd.cpu().numpy(), Rh)
+    x1, it1, rr1 = asm.pcg_solve(Rd, dofs, rel_tol=1e-13)  # rows skipped through the mask
+    asm.apply_dirichlet_k(dofs)
+    assert relerr(asm.to_scipy().toarray(), Kh.toarray()) < 1e-15
+    x2, it2, rr2 = asm.pcg_solve(Rd, dofs, rel_tol=1e-13)  # same after applyDirichletK
+    assert 0 < it1 < 5000 and rr1 <= 1e-13
+    assert torch.equal(x1, x2) and it1 == it2  # bitwise reproducible, independent of the (masked) Dirichlet rows
+    assert relerr(x1.cpu().numpy(), xh) < 1e-9
+    Rd0 = asm.apply_dirichlet_r(Rd.clone(), dofs)  # R[dirichlet] = 0 (:432-433)
+    assert not Rd0.cpu().numpy()[dofs].any()
+    xs, its, rrs = asm.pcg_solve_host(Rh, dofs, rel_tol=1e-13)
+    assert np.array_equal(xs, x1.cpu().numpy())
+
+
+def test_surface_pressure_matches_oracle():
+    from oracle import port
+
+    n = (4, 3, 5)
+    asm, coords, conn, rng = _assembled_box(n)
+    c0, conn0 = port.boxgen(*n, float(n[0]), float(n[1]), float(n[2]))
+    # every face of a few elements, plus a whole mesh face (x = lX: Abaqus face 6 of BoxGen elements? use all six ids on element sets)
+    elems, faces = [], []
+    for e in (0, 7, 19, conn.shape[0] - 1):
+        for f in range(1, 7):
+            elems.append(e)
+            faces.append(f)
+    ref = port.surface_pressure(coords, conn, elems, faces, 0.37)
+    got = asm.surface_pressure_host(elems, faces, 0.37)
+    assert relerr(got, ref) < 1e-13
+    # closed surface of one element: the resultant of a uniform pressure vanishes
+    one = asm.surface_pressure_host([5] * 6, list(range(1, 7)), 1.0).reshape(-1, 3).sum(axis=0)
+    assert np.abs(one).max() < 1e-13
