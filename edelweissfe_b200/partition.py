@@ -215,6 +215,8 @@ class SlabAssembly:
                                               C.c_void_p(base + 8 * (self._peer_head + lay.planeDofs))))
             a.assemble(flags)
             # orders the neighbour's peer stores before the interface add; every rank sees the same cut-back request
+            # NCCL has no bitwise reductions: MAX gives every rank the SAME word, in which an error bit (4: internal, 8: inverted
+            # element) outranks the cut-back bit (1) — errors abort the step on all ranks, a cut-back alone reaches all ranks as 1
             dist.all_reduce(self.status, op=dist.ReduceOp.MAX, group=group)
             if lay.has_lower:
                 self.recv, self.recvP, self.recvF = self._views[par]
@@ -226,6 +228,42 @@ class SlabAssembly:
             check(a.lib.ewb_interface_add(p(self.indptr), lay.planeDofs, p(a.csr_data), p(self.recv), p(a.P), p(a.F), p(self.recvP), p(self.recvF),
                                           a._stream()))
         self.step += 1
+
+    def compute_host(self, U, dU, flags=0, group=None):
+        """ElementAssembly.compute_host for one rank's slab: pinned host U, dU (local numbering) in, (P, F) out; the matrix (owned
+        rows + lower halo block) and the Gauss-point state stay on the device."""
+        a = self.asm
+        hU, hdU = a._pinned("U", a.nDof), a._pinned("dU", a.nDof)
+        hU.numpy()[:] = U
+        hdU.numpy()[:] = dU
+        a.U.copy_(hU, non_blocking=True)
+        a.dU.copy_(hdU, non_blocking=True)
+        self.assemble(flags, group)
+        hP, hF = a._pinned("P", a.nDof), a._pinned("F", a.nDof)
+        hP.copy_(a.P, non_blocking=True)
+        hF.copy_(a.F, non_blocking=True)
+        self.poll(group)
+        return hP.numpy().copy(), hF.numpy().copy()
+
+    def poll(self, group=None):
+        """Synchronise; every rank takes the same cut-back decision (nonlinearimplicitstatic.py:253-262): in the "peer" exchange the
+        status words were combined by the all-reduce of assemble(); the "nccl" exchange reduces a flag here."""
+        import torch
+        import torch.distributed as dist
+
+        from .assembly import CutbackRequest
+
+        if self.exchange != "nccl" or self.layout.world == 1:
+            return self.asm.poll()
+        failed = 0
+        try:
+            self.asm.poll()
+        except CutbackRequest:
+            failed = 1
+        flag = torch.tensor([failed], dtype=torch.int32, device=self.asm.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag.item()):
+            raise CutbackRequest("Von Mises Newton failed.", 0.5)
 
     # owned part of the distributed system (rows of owned dofs, local column numbering + lower halo block in self.recv)
     def owned_slices(self):
@@ -242,3 +280,67 @@ def interface_add_host(indptr, n_rows, data, recv, P, F, rP, rF):
         data[r0 : r0 + half] += recv[r0 + half : r1]
     P[:n_rows] += rP
     F[:n_rows] += rF
+
+
+def slab_parity_check(world, rank, device, n=None, elType="C3D8", material="vonmises", props=(2.1e4, 0.22, 355.0, 1000.0, 200.0, 1400.0), group=None):
+    """Slab-partitioned assembly of a small box on `world` ranks against the single-GPU assembly of the same box (computed on
+    rank 0): owned CSR rows, the lower halo block, P and F.  Returns the largest relative error on rank 0 (None elsewhere).
+    Collective: every rank of the group must call it.  Used by bench.py (--gpus N > 1) and tests/test_gpu_multi.py."""
+    import scipy.sparse as sp
+    import torch
+    import torch.distributed as dist
+
+    from .assembly import ElementAssembly
+    from .boxgen import box_mesh
+
+    n = n or (3 * world + 1, 6, 5)
+    lengths = (float(n[0]), float(n[1]), float(n[2]))
+    coords, conn = box_mesh(*n, lX=lengths[0], lY=lengths[1], lZ=lengths[2], elType=elType)
+    rng = np.random.default_rng(3)
+    coords = coords + 0.1 * rng.uniform(-1, 1, coords.shape)
+    dU = 4e-3 * rng.standard_normal(3 * coords.shape[0])
+    slab = SlabAssembly(n, lengths, elType, material, list(props), rank, world, device, group=group)
+    lay, asm = slab.layout, slab.asm
+    n0 = lay.node_offset()
+    asm.coords.copy_(torch.as_tensor(coords[n0 : n0 + lay.nNodeLoc]))
+    ldU = dU[3 * n0 : 3 * (n0 + lay.nNodeLoc)]
+    asm.U.copy_(torch.as_tensor(ldU))
+    asm.dU.copy_(torch.as_tensor(ldU))
+    for _ in range(3):  # repeated assemblies: the double-buffered receive side must stay consistent
+        slab.assemble(group=group)
+    slab.poll(group)
+    rows, nnzs = slab.owned_slices()
+    mine = (rank, 3 * n0, slab.indptr_host[: lay.ownedDofs + 1].copy(), slab.indices.cpu().numpy()[nnzs], asm.csr_data.cpu().numpy()[nnzs],
+            asm.P.cpu().numpy()[rows], asm.F.cpu().numpy()[rows], slab.recv.cpu().numpy(), lay.planeDofs, lay.has_lower, slab.exchange)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0, group=group)
+    slab.close()
+    if rank != 0:
+        return None
+    ref = ElementAssembly(elType, conn, coords, material, list(props), device=device, box=n)
+    ref.U.copy_(torch.as_tensor(dU))
+    ref.dU.copy_(torch.as_tensor(dU))
+    ref.assemble()
+    ref.poll()
+    Kg = ref.to_scipy()
+    Pg, Fg = ref.P.cpu().numpy(), ref.F.cpu().numpy()
+    nG = Kg.shape[0]
+    scale = abs(Kg).max()
+    worst = 0.0
+    for _r, off, indptr, indices, data, P, F, recv, planeDofs, has_lower, _ex in gathered:
+        nrows = indptr.size - 1
+        Kl = sp.csr_matrix((data, indices.astype(np.int64) + off, indptr), shape=(nrows, nG))
+        Kref = Kg[off : off + nrows]
+        if has_lower:  # the dx=-1 columns live in the halo block: compare them with the received rows
+            lowcols = np.arange(off - planeDofs, off)
+            halo = Kref[:planeDofs][:, lowcols]
+            Kref = Kref.tolil()
+            Kref[:planeDofs, lowcols] = 0
+            Kref = Kref.tocsr()
+            got = [recv[indptr[r] : indptr[r] + (indptr[r + 1] - indptr[r]) // 2] for r in range(planeDofs)]
+            halo.sort_indices()
+            worst = max(worst, float(np.abs(np.concatenate(got) - halo.data).max() / scale))
+        worst = max(worst, float(abs(Kl - Kref).max() / scale))
+        worst = max(worst, float(np.abs(P - Pg[off : off + nrows]).max() / np.abs(Pg).max()))
+        worst = max(worst, float(np.abs(F - Fg[off : off + nrows]).max() / np.abs(Fg).max()))
+    return worst
