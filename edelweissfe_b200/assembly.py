@@ -263,15 +263,19 @@ class ElementAssembly:
 
     def compute_host(self, U, dU, stateRef_aos=None, stateTemp_aos=None, time=(0.0, 0.0), dT=0.0, flags=0):
         """computeElements with HOST arrays (what the solver plugin calls): U, dU [nDof] in, (P, F) out; K stays on the device
-        (csr_data_host() / the device solver consume it).  Raises CutbackRequest.
+        (csr_data_host() / the device solver consume it).  Raises CutbackRequest.  The returned arrays are views of pinned buffers
+        that the next call overwrites (the plugin adds them to the solver's vectors at once).
 
         Gauss-point state is DEVICE RESIDENT by default: the pass reads state_ref and writes state_temp on the device, and the
         caller commits with accept_last_state() / reads back with download_state_temp() when an increment is accepted — per Newton
         iteration only 2 + 2 dof vectors cross PCIe.  Passing stateRef_aos / stateTemp_aos ([nEl, nGp, nState], the reference's
         per-element layout) restores the stateless form: stateRef is uploaded before and stateTemp downloaded after the pass."""
         hU, hdU = self._pinned("U", self.nDof), self._pinned("dU", self.nDof)
-        hU.numpy()[:] = U
-        hdU.numpy()[:] = dU
+        # U / dU None: the caller has filled the pinned input buffers of host_io() in place (no staging copy)
+        if U is not None:
+            hU.numpy()[:] = U
+        if dU is not None:
+            hdU.numpy()[:] = dU
         self.U.copy_(hU, non_blocking=True)
         self.dU.copy_(hdU, non_blocking=True)
         if stateRef_aos is not None:
@@ -285,7 +289,11 @@ class ElementAssembly:
         self.poll()
         if stateTemp_aos is not None:
             np.asarray(stateTemp_aos).reshape(-1)[:] = self._pinned("S", self.nEl * self.nGp * self.nState).numpy()
-        return hP.numpy().copy(), hF.numpy().copy()
+        return hP.numpy(), hF.numpy()  # views of the pinned output buffers: valid until the next call
+
+    def host_io(self):
+        """Pinned host buffers of compute_host as NumPy views: (U, dU) inputs a caller may fill in place, (P, F) outputs."""
+        return tuple(self._pinned(k, self.nDof).numpy() for k in ("U", "dU", "P", "F"))
 
     def _aos_device_scratch(self):
         scratch = getattr(self, "_aos_scratch", None)

@@ -234,8 +234,10 @@ class SlabAssembly:
         rows + lower halo block) and the Gauss-point state stay on the device."""
         a = self.asm
         hU, hdU = a._pinned("U", a.nDof), a._pinned("dU", a.nDof)
-        hU.numpy()[:] = U
-        hdU.numpy()[:] = dU
+        if U is not None:  # None: the pinned input buffers (ElementAssembly.host_io) were filled in place
+            hU.numpy()[:] = U
+        if dU is not None:
+            hdU.numpy()[:] = dU
         a.U.copy_(hU, non_blocking=True)
         a.dU.copy_(hdU, non_blocking=True)
         self.assemble(flags, group)
@@ -243,7 +245,7 @@ class SlabAssembly:
         hP.copy_(a.P, non_blocking=True)
         hF.copy_(a.F, non_blocking=True)
         self.poll(group)
-        return hP.numpy().copy(), hF.numpy().copy()
+        return hP.numpy(), hF.numpy()
 
     def poll(self, group=None):
         """Synchronise; every rank takes the same cut-back decision (nonlinearimplicitstatic.py:253-262): in the "peer" exchange the
