@@ -41,6 +41,36 @@ int fail(int code, const std::string& msg) {
         if (_e != cudaSuccess) return fail(EWB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
     } while (0)
 
+// Makes `device` current for the duration of an entry point and restores the caller's device afterwards (the host layer —
+// torch — must not find its current device changed by a call into this library).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define WITH_DEVICE(dev)                                                                                      \
+    DeviceGuard _guard(dev);                                                                                  \
+    if (_guard.err != cudaSuccess) return fail(EWB_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(_guard.err))
+
+// device that owns a device pointer (entry points without a plan)
+int deviceOf(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        int d = 0;
+        cudaGetDevice(&d);
+        return d;
+    }
+    return a.device;
+}
+
 template <class T>
 int upload(T** dst, const std::vector<T>& v) {
     CUDA_TRY(cudaMalloc((void**)dst, std::max<size_t>(v.size(), 1) * sizeof(T)));
@@ -172,12 +202,20 @@ int ewb_plan_create(ewb_plan** out, int el_type, int64_t n_el, int64_t n_node, c
     int nn, ngp;
     if (int rc = elementInfo(el_type, &nn, &ngp)) return rc;
     if (n_el * nn >= (int64_t)1 << 31) return fail(EWB_ERR_UNSUPPORTED, "too many element nodes for int32 incidence");
-    CUDA_TRY(cudaSetDevice(device));
+    WITH_DEVICE(device);
     auto* p = new ewb_plan();
     p->device = device; p->elType = el_type; p->nn = nn; p->ngp = ngp; p->nEl = n_el; p->nNode = n_node;
     p->connHost.assign(conn_host, conn_host + n_el * nn);
     for (int64_t i = 0; i < n_el * nn; ++i)
         if (conn_host[i] < 0 || conn_host[i] >= n_node) { delete p; return fail(EWB_ERR_ARG, "connectivity index out of range"); }
+    // collapsed elements (a node listed twice) would make two local nodes share one CSR slot in the row gather: not supported
+    for (int64_t e = 0; e < n_el; ++e)
+        for (int a = 1; a < nn; ++a)
+            for (int b = 0; b < a; ++b)
+                if (conn_host[e * nn + a] == conn_host[e * nn + b]) {
+                    delete p;
+                    return fail(EWB_ERR_UNSUPPORTED, "element " + std::to_string(e) + " lists a node twice (collapsed elements are not supported)");
+                }
 
     // node -> incident (element, local node), ascending element (counting sort)
     std::vector<int64_t> incPtr(n_node + 1, 0);
@@ -242,7 +280,7 @@ int ewb_plan_create(ewb_plan** out, int el_type, int64_t n_el, int64_t n_node, c
 
 void ewb_plan_destroy(ewb_plan* p) {
     if (!p) return;
-    cudaSetDevice(p->device);
+    DeviceGuard guard(p->device);
     cudaFree(p->conn); cudaFree(p->adjPtr); cudaFree(p->adj); cudaFree(p->incPtr); cudaFree(p->inc);
     cudaFree(p->failFlag); cudaFree(p->peScratch); cudaFree(p->vijScratch); cudaFree(p->gatherOrder); cudaFree(p->gatherSlots);
     cudaFree(p->pcgWork); cudaFree(p->pcgPartial); cudaFree(p->pcgScal);
@@ -346,7 +384,7 @@ extern "C" {
 
 int ewb_plan_csr_pattern(const ewb_plan* p, int32_t* indptr_dev, int32_t* indices_dev, void* stream) {
     if (!p || !indptr_dev || !indices_dev) return fail(EWB_ERR_ARG, "ewb_plan_csr_pattern: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    WITH_DEVICE(p->device);
     const int B = 128;
     csrPatternKernel<<<(unsigned)((p->nNode + B - 1) / B), B, 0, (cudaStream_t)stream>>>(p->nNode, p->adjPtr, p->adj, indptr_dev, indices_dev);
     LAUNCH_CHECK();
@@ -355,7 +393,7 @@ int ewb_plan_csr_pattern(const ewb_plan* p, int32_t* indptr_dev, int32_t* indice
 
 int ewb_plan_slot_map(const ewb_plan* p, int64_t e0, int64_t e1, int32_t* x_dev, void* stream) {
     if (!p || !x_dev || e0 < 0 || e1 > p->nEl || e0 >= e1) return fail(EWB_ERR_ARG, "ewb_plan_slot_map: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    WITH_DEVICE(p->device);
     const int nd = 3 * p->nn;
     const int64_t total = (e1 - e0) * nd * nd;
     const int B = 256;
@@ -400,7 +438,7 @@ int ewb_plan_set_box(ewb_plan* p, int64_t nX, int64_t nY, int64_t nZ) {
 
 int ewb_plan_set_gather_order(ewb_plan* p, const int32_t* order_host) {
     if (!p) return fail(EWB_ERR_ARG, "null plan");
-    CUDA_TRY(cudaSetDevice(p->device));
+    WITH_DEVICE(p->device);
     if (!order_host) {
         cudaFree(p->gatherOrder);
         p->gatherOrder = nullptr;
@@ -420,7 +458,7 @@ int ewb_plan_set_gather_order(ewb_plan* p, const int32_t* order_host) {
 int ewb_compute_elements_vij(ewb_plan* p, int material, const double* props, int n_props, const ewb_buffers* b, double* pe_dev, int flags,
                              void* stream) {
     if (!p || !b || !props || !pe_dev) return fail(EWB_ERR_ARG, "ewb_compute_elements_vij: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    WITH_DEVICE(p->device);
     ewb::MatParams mp; int mc, nms;
     if (int rc = materialClass(p->elType, material, props, n_props, &mp, &mc, &nms)) return rc;
     double* V = (flags & EWB_FLAG_NO_STIFFNESS) ? nullptr : b->vij;
@@ -429,7 +467,7 @@ int ewb_compute_elements_vij(ewb_plan* p, int material, const double* props, int
 
 int ewb_update_csr(ewb_plan* p, const double* vij_dev, double* csr_data_dev, void* stream) {
     if (!p || !vij_dev || !csr_data_dev) return fail(EWB_ERR_ARG, "ewb_update_csr: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    WITH_DEVICE(p->device);
     const int B = 128;
     const unsigned grid = (unsigned)((p->nSlots + B - 1) / B);
     if (p->nn == 8)
@@ -447,7 +485,7 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
     if (!b->coords || !b->U || !b->dU || !b->state_ref || !b->state_temp || !b->P || !b->F) return fail(EWB_ERR_ARG, "ewb_assemble: null buffer");
     const bool wantK = !(flags & EWB_FLAG_NO_STIFFNESS);
     if (wantK && !b->csr_data) return fail(EWB_ERR_ARG, "ewb_assemble: csr_data is null");
-    CUDA_TRY(cudaSetDevice(p->device));
+    WITH_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     ewb::MatParams mp; int mc, nms;
     if (int rc = materialClass(p->elType, material, props, n_props, &mp, &mc, &nms)) return rc;
@@ -519,7 +557,7 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
 
 int ewb_body_force(ewb_plan* p, const double* coords_dev, const double load_host[3], double* pext_dev, void* stream) {
     if (!p || !coords_dev || !load_host || !pext_dev) return fail(EWB_ERR_ARG, "ewb_body_force: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    WITH_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int nd = 3 * p->nn;
     if (!p->peScratch) CUDA_TRY(cudaMalloc((void**)&p->peScratch, (size_t)p->nEl * nd * sizeof(double)));
@@ -543,7 +581,7 @@ int ewb_body_force(ewb_plan* p, const double* coords_dev, const double load_host
 
 int ewb_poll_status(ewb_plan* p, void* stream, double* pNewDT) {
     if (!p) return fail(EWB_ERR_ARG, "null plan");
-    CUDA_TRY(cudaSetDevice(p->device));
+    WITH_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemcpyAsync(p->failHost, p->failFlag, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemsetAsync(p->failFlag, 0, sizeof(int), st));
@@ -572,6 +610,7 @@ int64_t ewb_debug_timing(ewb_plan* p, long long* out_host, int64_t n) {
 
 int ewb_state_to_soa(const double* aos, double* soa, int64_t nEl, int nGp, int nState, void* stream) {
     if (!aos || !soa) return fail(EWB_ERR_ARG, "null state buffer");
+    WITH_DEVICE(deviceOf(soa));
     const int64_t total = nEl * nGp * nState;
     stateTransposeKernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(aos, soa, nEl, nGp, nState, 1);
     LAUNCH_CHECK();
@@ -580,6 +619,7 @@ int ewb_state_to_soa(const double* aos, double* soa, int64_t nEl, int nGp, int n
 
 int ewb_state_to_aos(const double* soa, double* aos, int64_t nEl, int nGp, int nState, void* stream) {
     if (!aos || !soa) return fail(EWB_ERR_ARG, "null state buffer");
+    WITH_DEVICE(deviceOf(soa));
     const int64_t total = nEl * nGp * nState;
     stateTransposeKernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(soa, aos, nEl, nGp, nState, 0);
     LAUNCH_CHECK();
@@ -639,6 +679,7 @@ int ewb_peer_close(void* ptr) {
 int ewb_interface_add(const int32_t* indptr_dev, int64_t n_rows, double* data, const double* recv, double* P, double* F, const double* rP,
                       const double* rF, void* stream) {
     if (!indptr_dev || !data || !recv || n_rows <= 0) return fail(EWB_ERR_ARG, "ewb_interface_add: bad arguments");
+    WITH_DEVICE(deviceOf(data));
     const int B = 256;
     const int64_t threads = n_rows * 32;
     interfaceAddKernel<<<(unsigned)((threads + B - 1) / B), B, 0, (cudaStream_t)stream>>>(indptr_dev, n_rows, data, recv, P, F, rP, rF);
@@ -649,7 +690,7 @@ int ewb_interface_add(const int32_t* indptr_dev, int64_t n_rows, double* data, c
 int ewb_apply_dirichlet_k(const ewb_plan* p, double* data, const int32_t* dofs_dev, int64_t n, void* stream) {
     if (!p || !data || (!dofs_dev && n > 0)) return fail(EWB_ERR_ARG, "ewb_apply_dirichlet_k: bad arguments");
     if (n == 0) return EWB_OK;
-    CUDA_TRY(cudaSetDevice(p->device));
+    WITH_DEVICE(p->device);
     dirichletKernel<<<(unsigned)n, 96, 0, (cudaStream_t)stream>>>(nullptr, p->adjPtr, p->adj, data, dofs_dev, n);
     LAUNCH_CHECK();
     return EWB_OK;
@@ -659,6 +700,7 @@ int ewb_apply_dirichlet_k(const ewb_plan* p, double* data, const int32_t* dofs_d
 int ewb_apply_dirichlet_r(double* r_dev, const int32_t* dofs_dev, const double* values_dev, int64_t n, void* stream) {
     if (!r_dev || (!dofs_dev && n > 0)) return fail(EWB_ERR_ARG, "ewb_apply_dirichlet_r: bad arguments");
     if (n == 0) return EWB_OK;
+    WITH_DEVICE(deviceOf(r_dev));
     ewb::dirichletRKernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(r_dev, dofs_dev, values_dev, n);
     LAUNCH_CHECK();
     return EWB_OK;
@@ -666,7 +708,7 @@ int ewb_apply_dirichlet_r(double* r_dev, const int32_t* dofs_dev, const double* 
 
 int ewb_spmv(const ewb_plan* p, const double* csr_data_dev, const double* x_dev, double* y_dev, void* stream) {
     if (!p || !csr_data_dev || !x_dev || !y_dev) return fail(EWB_ERR_ARG, "ewb_spmv: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    WITH_DEVICE(p->device);
     ewb::spmvNodeKernel<false, false><<<(unsigned)((p->nNode + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p->nNode, p->adjPtr, p->adj, csr_data_dev, x_dev, y_dev,
                                                                                                       nullptr, nullptr, nullptr);
     LAUNCH_CHECK();
@@ -676,7 +718,7 @@ int ewb_spmv(const ewb_plan* p, const double* csr_data_dev, const double* x_dev,
 int ewb_pcg_solve(ewb_plan* p, const double* A, const double* b, double* x, const int32_t* dirichlet_dofs_dev, int64_t n_dirichlet, double rel_tol,
                   int max_iter, int* iters_out, double* relres_out, void* stream) {
     if (!p || !A || !b || !x || (n_dirichlet > 0 && !dirichlet_dofs_dev) || max_iter < 0) return fail(EWB_ERR_ARG, "ewb_pcg_solve: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    WITH_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nDof = 3 * p->nNode;
     const int64_t nbV = (nDof + 255) / 256, nbS = (p->nNode + 7) / 8;
@@ -746,7 +788,7 @@ int ewb_surface_pressure(ewb_plan* p, const double* coords_dev, int64_t n_faces,
     if (!p || !coords_dev || !pext_dev || n_faces < 0 || (n_faces > 0 && (!elem_host || !face_host))) return fail(EWB_ERR_ARG, "ewb_surface_pressure: bad arguments");
     if (p->nn != 8) return fail(EWB_ERR_UNSUPPORTED, "ewb_surface_pressure: 4-node faces of 8-node hexahedra only");
     if (n_faces == 0) return EWB_OK;
-    CUDA_TRY(cudaSetDevice(p->device));
+    WITH_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     static const int faceNodes[6][4] = {{0, 3, 2, 1}, {4, 5, 6, 7}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}};
     // loaded nodes and their (face, local node) incidence in ascending order: fixed summation order

@@ -458,3 +458,34 @@ def test_surface_pressure_matches_oracle():
     # closed surface of one element: the resultant of a uniform pressure vanishes
     one = asm.surface_pressure_host([5] * 6, list(range(1, 7)), 1.0).reshape(-1, 3).sum(axis=0)
     assert np.abs(one).max() < 1e-13
+
+
+def test_collapsed_element_rejected():
+    """A node listed twice in an element would make two local nodes share a CSR slot in the row gather: refused at plan creation."""
+    from edelweissfe_b200 import ElementAssembly, box_mesh
+    from edelweissfe_b200._lib import EwbError
+
+    coords, conn = box_mesh(2, 2, 2)
+    conn = conn.copy()
+    conn[3, 5] = conn[3, 1]
+    with pytest.raises(EwbError, match="lists a node twice"):
+        ElementAssembly("C3D8", conn, coords, "linearelastic", [2.1e4, 0.22])
+
+
+def test_current_device_is_preserved():
+    """Entry points make the plan's device current only for the duration of the call."""
+    import torch
+
+    from edelweissfe_b200 import ElementAssembly, box_mesh
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    coords, conn = box_mesh(3, 3, 3)
+    torch.cuda.set_device(0)
+    asm = ElementAssembly("C3D8", conn, coords, "linearelastic", [2.1e4, 0.22], device="cuda:1", box=(3, 3, 3))
+    with torch.cuda.device(1):
+        asm.assemble()
+        asm.poll()
+        s = asm.state_aos("temp")
+    assert torch.cuda.current_device() == 0
+    assert s.device.index == 1 and bool(torch.isfinite(asm.csr_data).all())
