@@ -49,7 +49,7 @@ __device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity, volatil
     int spins = 0;
     while (!mbarTryWait(bar, parity)) {
         if (*abortFlag) return;
-        if (++spins > (1 << 20)) {
+        if (++spins > (1 << 17)) {
             *abortFlag = 1;
             atomicOr(failFlag, 4);
             return;
@@ -96,6 +96,9 @@ struct RowPipeLayout {
 template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0, int RECST = 2>
 __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const SweepArgs A) {
     static_assert(RP == 0 || (NPW % 4 == 0 && NTW % 4 == 0 && NGW % 4 == 0), "setmaxnreg works on warp groups");
+    // A P warp's consecutive tasks are NPW / HALVES rows apart and wait on the parity of a record stage only: the wait is
+    // unambiguous as long as the warp cannot be two phases ahead of the T warps, i.e. row stride <= number of record stages.
+    static_assert((NPW + (TZ + 1) / 4 - 1) / ((TZ + 1) / 4) <= RECST, "row stride of the producer warps must not exceed the record ring depth");
     constexpr int REG0 = (65536 / ((NPW + NTW + NGW) * 32)) / 8 * 8;  // registers per thread at launch
     using L = RowPipeLayout<MC, TL, TZ, NPW, RECST>;
     using R = RecLayout<MC>;
@@ -671,6 +674,8 @@ int launchRowPipeVariant(SweepPlan& sp, int variant, const MatParams& mp, const 
         case 1040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120>(sp, mp, b, failFlag, flags, st);
         case 2040404: return launchRowPipe<MC, TL, 7, 4, 4, 4, 0, 0, 0, 3>(sp, mp, b, failFlag, flags, st);
         case 4040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 152, 128, 104, 3>(sp, mp, b, failFlag, flags, st);
+        case 5080404: return launchRowPipe<MC, TL, 7, 8, 4, 4, 152, 128, 80, 4>(sp, mp, b, failFlag, flags, st);
+        case 7080404: return launchRowPipe<MC, TL, 7, 8, 4, 4, 144, 144, 80, 4>(sp, mp, b, failFlag, flags, st);
 #endif
         case 40404: return launchRowPipe<MC, TL, 7, 4, 4, 4>(sp, mp, b, failFlag, flags, st);
 #ifdef EWB_VARIANTS

@@ -90,6 +90,31 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
+// Tile-transpose identity.  Every product accumulated here has the form M[(i,a),(j,b)] = sum_gp c u_a,i v_b,j with u == v (or the
+// sum of two such terms with the roles swapped), so tile (j,i) is the transpose of tile (i,j) in the node indices:
+// M[(j,a),(i,b)] = M[(i,b),(j,a)].  Only the tiles i <= j are computed on the tensor pipe (6 instead of 9 DMMA per k-step); the
+// lane (row r, q) obtains its entries of tile (j,i), columns 2q + t, from lane (row 2q + t, q' = r >> 1), slot r & 1, of tile (i,j).
+// Measured on B200 (round 2): parity green, but SLOWER in every kernel (LE 598 -> 590, von Mises 334 -> 324, Neo-Hooke 413 -> 395
+// Melem/s): the 24 shuffles per accumulator set sit on the warp's critical path, while the FP64 pipe was not the binding unit.
+// Off by default; -DEWB_TILE_SYMMETRY=1 enables it.
+#ifndef EWB_TILE_SYMMETRY
+#define EWB_TILE_SYMMETRY 0
+#endif
+__device__ __forceinline__ void mirrorTiles(double (&c)[3][3][2], int lane) {
+    const int r = lane >> 2, q = lane & 3;
+    const int src0 = 4 * (2 * q) + (r >> 1), src1 = src0 + 4;
+    const bool odd = r & 1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 3; ++j) {
+            const double a0 = __shfl_sync(0xffffffffu, c[i][j][0], src0), a1 = __shfl_sync(0xffffffffu, c[i][j][1], src0);
+            const double b0 = __shfl_sync(0xffffffffu, c[i][j][0], src1), b1 = __shfl_sync(0xffffffffu, c[i][j][1], src1);
+            c[j][i][0] = odd ? a1 : a0;
+            c[j][i][1] = odd ? b1 : b0;
+        }
+}
+
 // local node a of a BoxGen Hexa8: offsets (dx,dy,dz) (generators/boxgen.py:172-185)
 __device__ __forceinline__ int ndx(int a) { return (a >> 1) & 1; }
 __device__ __forceinline__ int ndy(int a) { return (a >> 2) & 1; }
@@ -307,10 +332,11 @@ __device__ __forceinline__ void elementTiles(const double* T, int lane, const do
                 for (int i = 0; i < 3; ++i) {
                     const double ai = w * g[ks][i];
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) dmma(c[i][j], ai, g[ks][j]);
+                    for (int j = EWB_TILE_SYMMETRY ? i : 0; j < 3; ++j) dmma(c[i][j], ai, g[ks][j]);
                 }
             }
         }
+        if (EWB_TILE_SYMMETRY && wantK) mirrorTiles(c, lane);
     } else if constexpr (MC == MC_VM) {
         auto& c1 = acc.c1;
         auto& c2 = acc.c2;
@@ -336,7 +362,7 @@ __device__ __forceinline__ void elementTiles(const double* T, int lane, const do
                 for (int i = 0; i < 3; ++i) {
                     const double mi = cm * g[ks][i];
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) dmma(c2[i][j], mi, g[ks][j]);
+                    for (int j = EWB_TILE_SYMMETRY ? i : 0; j < 3; ++j) dmma(c2[i][j], mi, g[ks][j]);
                 }
             } else if (wantK) {
                 // p_a = B_a^T n = N g_a, N = tensor(n)  (n Voigt 11,22,33,12,13,23)
@@ -348,13 +374,17 @@ __device__ __forceinline__ void elementTiles(const double* T, int lane, const do
                 for (int i = 0; i < 3; ++i) {
                     const double li = cl * g[ks][i], mi = cm * g[ks][i], ri = ca * pv[i];
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
+                    for (int j = EWB_TILE_SYMMETRY ? i : 0; j < 3; ++j) {
                         dmma(c1[i][j], li, g[ks][j]);
                         dmma(c1[i][j], ri, pv[j]);
                         dmma(c2[i][j], mi, g[ks][j]);
                     }
                 }
             }
+        }
+        if (EWB_TILE_SYMMETRY && wantK) {
+            mirrorTiles(c2, lane);
+            if (!acc.elastic) mirrorTiles(c1, lane);  // warp uniform
         }
     } else {
         auto& c1 = acc.c1;
@@ -389,7 +419,7 @@ __device__ __forceinline__ void elementTiles(const double* T, int lane, const do
                     for (int j = 0; j < 3; ++j) {
                         if (i == j) {
                             dmma(c1[i][i], a1 + a2, nv[i]);
-                        } else {
+                        } else if (!EWB_TILE_SYMMETRY || j > i) {
                             dmma(c1[i][j], a1, nv[j]);
                             dmma(c2[i][j], a2, nv[j]);
                         }
@@ -402,12 +432,16 @@ __device__ __forceinline__ void elementTiles(const double* T, int lane, const do
 #pragma unroll
                     for (int i = 0; i < 3; ++i)
 #pragma unroll
-                        for (int j = 0; j < 3; ++j) {
+                        for (int j = EWB_TILE_SYMMETRY ? i : 0; j < 3; ++j) {
                             dmma(c1[i][j], k4 * fv[i], nv[j]);
                             dmma(c1[i][j], k4 * nv[i], fv[j]);
                         }
                 }
             }
+        }
+        if (EWB_TILE_SYMMETRY && wantK) {
+            mirrorTiles(c1, lane);
+            mirrorTiles(c2, lane);
         }
     }
     // reduce the residual row over the 4 lanes (Gauss-point pairs) of the row
@@ -443,9 +477,10 @@ __device__ __forceinline__ void elementTilesH(const double* T, int lane, bool wa
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
-                for (int j = 0; j < 3; ++j) dmma(c[i][j], h[ks][i], h[ks][j]);
+                for (int j = EWB_TILE_SYMMETRY ? i : 0; j < 3; ++j) dmma(c[i][j], h[ks][i], h[ks][j]);
         }
     }
+    if (EWB_TILE_SYMMETRY && wantK) mirrorTiles(c, lane);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         Pr[i] += __shfl_xor_sync(0xffffffffu, Pr[i], 1);
