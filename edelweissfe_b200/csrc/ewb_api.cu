@@ -497,7 +497,7 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
         if (!p->sweep.indexable()) return fail(EWB_ERR_UNSUPPORTED, "ewb_assemble: the fused BoxGen kernels index nodes with int32 (3 * nodes < 2^31); use EWB_FLAG_FORCE_GENERIC");
         // automatic choice (B200, round 2): linear elasticity runs the row-pipelined kernel (598 vs 551 Melem/s at 100^3); von Mises and
         // Neo-Hooke, whose phase A is heavier than four producer warps can feed, stay on the first-generation sweep (334 vs 307, 413 vs 352)
-        const int variant = p->fusedVariant != 0 ? p->fusedVariant : (mc == ewb::MC_LE ? 3040804 : 1);
+        const int variant = p->fusedVariant != 0 ? p->fusedVariant : (mc == ewb::MC_LE ? 4040804 : 1);
         const bool v1 = (flags & EWB_FLAG_SWEEP_V1) || variant == 1;
         const int rc = v1 ? p->sweep.launchV1(p->elType, mc, mp, b, p->failFlag, flags, st)
                           : ewb::launchRowPipeAny(p->sweep, variant, p->elType, mc, mp, b, p->failFlag, flags, st);

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
                             }
                         }
                     }
-#ifndef EWB_NO_STATE_PREFETCH
+#ifndef EWB_NO_STATE_PREFETCH  // L2 prefetch of the next task's Gauss-point state (622 -> 647 Melem/s once the producers are the critical role)
                     const int k = 4 * p.h + ak, ez = z0 - 1 + k;
                     if (ez >= 0 && ez < A.nZ && k <= nz) {
                         const double* sp = A.stateRef + (((int64_t)exs * A.nY + ey) * A.nZ + ez) * 8 + agp;
@@ -267,14 +267,12 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
             }
         };
         if constexpr (!HREC) setShapeDerivs(0);
-        double Kp0[9], Kp1[9];  // CHAIN: the previous element row's blocks of this warp's element position
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Kp0[i] = Kp1[i] = 0.0;
         const bool wantK = A.wantK != 0;
         RP_DECL();
-#pragma unroll 1
-        for (int n = 0; n < nRows; ++n) {
-            const int s = n / rowsPerStep, jj = n - s * rowsPerStep;
+        // One element row: tiles -> blocks (Kc), chained with the previous row's blocks (Kq) of the same element position.  The two
+        // register sets swap roles every row (the loop below is unrolled by two), so the chaining costs no register moves.
+        int jj = 0;  // element row inside the plane step, advanced incrementally (no division per row)
+        auto row = [&](int n, double (&Kc0)[9], double (&Kc1)[9], const double (&Kq0)[9], const double (&Kq1)[9]) {
             const int ey = y0 - 1 + jj;
             const int rs = n % L::REC_STAGES, ss = n % L::SLOT_STAGES;
             RP_T0();
@@ -287,27 +285,23 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
             for (int k = tw; k < NE; k += NTW) {
                 const int ez = z0 - 1 + k;
                 const bool valid = ey >= 0 && ey < A.nY && ez >= 0 && ez < A.nZ && k <= nz;  // warp uniform
-                double K0[9], K1[9], Pr[3];
+                double Pr[3];
                 if (valid) {
                     const double* T = records + (size_t)(rs * NE + k) * PEL;
                     TileAcc<MC> acc;
                     if constexpr (HREC) elementTilesH(T, lane, wantK, acc, Pr);
                     else elementTiles<MC>(T, lane, dNl, A.mp, wantK, acc, Pr);
-                    finishBlock<MC>(acc, 0, A.mp, K0);
-                    finishBlock<MC>(acc, 1, A.mp, K1);
-                }
-                if constexpr (CHAIN) {
-                    if (valid) {
+                    finishBlock<MC>(acc, 0, A.mp, Kc0);
+                    finishBlock<MC>(acc, 1, A.mp, Kc1);
+                    if constexpr (CHAIN) {
                         if (jj != 0 && (bRow >> 2) == flip && (bq >> 1) == flip) {  // both nodes on the face shared with the previous row
 #pragma unroll
-                            for (int i = 0; i < 9; ++i) { K0[i] += Kp0[i]; K1[i] += Kp1[i]; }
+                            for (int i = 0; i < 9; ++i) { Kc0[i] += Kq0[i]; Kc1[i] += Kq1[i]; }
                         }
-#pragma unroll
-                        for (int i = 0; i < 9; ++i) { Kp0[i] = K0[i]; Kp1[i] = K1[i]; }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 9; ++i) Kp0[i] = Kp1[i] = 0.0;
                     }
+                } else if constexpr (CHAIN) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) Kc0[i] = Kc1[i] = 0.0;  // nothing to chain into the next row
                 }
                 if (!slotReady) {
                     RP_LAP(2);
@@ -319,15 +313,15 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
                     double* slot = slots + (size_t)(ss * NE + k) * SLOT_EL;
                     if (wantK) {
                         double2* dst = reinterpret_cast<double2*>(slot + lane * 18);
-                        dst[0] = make_double2(K0[0], K0[1]);
-                        dst[1] = make_double2(K0[2], K0[3]);
-                        dst[2] = make_double2(K0[4], K0[5]);
-                        dst[3] = make_double2(K0[6], K0[7]);
-                        dst[4] = make_double2(K0[8], K1[0]);
-                        dst[5] = make_double2(K1[1], K1[2]);
-                        dst[6] = make_double2(K1[3], K1[4]);
-                        dst[7] = make_double2(K1[5], K1[6]);
-                        dst[8] = make_double2(K1[7], K1[8]);
+                        dst[0] = make_double2(Kc0[0], Kc0[1]);
+                        dst[1] = make_double2(Kc0[2], Kc0[3]);
+                        dst[2] = make_double2(Kc0[4], Kc0[5]);
+                        dst[3] = make_double2(Kc0[6], Kc0[7]);
+                        dst[4] = make_double2(Kc0[8], Kc1[0]);
+                        dst[5] = make_double2(Kc1[1], Kc1[2]);
+                        dst[6] = make_double2(Kc1[3], Kc1[4]);
+                        dst[7] = make_double2(Kc1[5], Kc1[6]);
+                        dst[8] = make_double2(Kc1[7], Kc1[8]);
                     }
                     if (bq == 0) {
                         slot[576 + 3 * bRow] = Pr[0];
@@ -341,6 +335,15 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
             mbarArrive(recEmpty + rs);
             mbarArrive(slotFull + ss);
             RP_LAP(3);
+            if (++jj == rowsPerStep) jj = 0;
+        };
+        double Ka0[9], Ka1[9], Kb0[9], Kb1[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Ka0[i] = Ka1[i] = Kb0[i] = Kb1[i] = 0.0;
+#pragma unroll 1
+        for (int n = 0; n < nRows; n += 2) {
+            row(n, Ka0, Ka1, Kb0, Kb1);
+            if (n + 1 < nRows) row(n + 1, Kb0, Kb1, Ka0, Ka1);
         }
         RP_FLUSH(nRows);
         return;
@@ -385,10 +388,11 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
     const double* zeroPad = smem + L::OFF_ZERO;
 
     RP_DECL();
+    int jjNext = 0, exNext = exBegin;  // advanced incrementally (no division per row)
 #pragma unroll 1
     for (int n = 0; n < nRows; ++n) {
-        const int s = n / rowsPerStep, jj = n - s * rowsPerStep;
-        const int ex = exBegin + s;
+        const int jj = jjNext, ex = exNext;
+        if (++jjNext == rowsPerStep) { jjNext = 0; ++exNext; }
         const int ss = n % L::SLOT_STAGES;
         RP_T0();
         mbarWait(slotFull + ss, (n / L::SLOT_STAGES) & 1, abortFlag, A.failFlag);
@@ -673,16 +677,16 @@ int launchRowPipeVariant(SweepPlan& sp, int variant, const MatParams& mp, const 
         case 30405: return launchRowPipe<MC, TL, 7, 3, 4, 5>(sp, mp, b, failFlag, flags, st);
         case 1040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120>(sp, mp, b, failFlag, flags, st);
         case 2040404: return launchRowPipe<MC, TL, 7, 4, 4, 4, 0, 0, 0, 3>(sp, mp, b, failFlag, flags, st);
-        case 4040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 152, 128, 104, 3>(sp, mp, b, failFlag, flags, st);
         case 5080404: return launchRowPipe<MC, TL, 7, 8, 4, 4, 152, 128, 80, 4>(sp, mp, b, failFlag, flags, st);
         case 7080404: return launchRowPipe<MC, TL, 7, 8, 4, 4, 144, 144, 80, 4>(sp, mp, b, failFlag, flags, st);
 #endif
         case 40404: return launchRowPipe<MC, TL, 7, 4, 4, 4>(sp, mp, b, failFlag, flags, st);
 #ifdef EWB_VARIANTS
         case 2040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120, 3>(sp, mp, b, failFlag, flags, st);
+        case 3040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 120, 104, 3>(sp, mp, b, failFlag, flags, st);
 #endif
-        case 3040804:
-        default: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 120, 104, 3>(sp, mp, b, failFlag, flags, st);
+        case 4040804:
+        default: return launchRowPipe<MC, TL, 7, 4, 8, 4, 152, 128, 104, 3>(sp, mp, b, failFlag, flags, st);
     }
 }
 

@@ -201,7 +201,11 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
             if (!(wd > 0.0)) atomicOr(failFlag, 8);  // sqrt(w detJ): inverted element
             const double sq = sqrt(wd);
             const int ks = gp >> 2, q = gp & 3;
-            double* Hq = rec + ks * RecLayoutH::KS + q;  // rowFlip16 = 16: the y bit of the row index is inverted (row-pipelined kernel, odd element rows)
+            // rowFlip16 = 16: the y bit of the row index is inverted (row-pipelined kernel, odd element rows); two bases keep every
+            // store offset an immediate
+            double* Hq = rec + ks * RecLayoutH::KS + q;
+            double* HqLo = Hq + rowFlip16;  // rows 0..3 move up by four rows
+            double* HqHi = Hq - rowFlip16;  // rows 4..7 move down
             forNodes<8>([&](auto ic) {
                 constexpr int a = decltype(ic)::value;
                 constexpr int r = (0x67542310u >> (4 * a)) & 7;  // rowNode is an involution: row of node a
@@ -209,7 +213,7 @@ __device__ __forceinline__ void gaussPointCompact(double* rec, const double* stg
                 shapeDeriv<8, a>(xi, eta, zeta, d);
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    Hq[2 * c * RecLayoutH::KS + 4 * r + (r < 4 ? rowFlip16 : -rowFlip16)] = sq * (iJ[c * 3] * d[0] + iJ[c * 3 + 1] * d[1] + iJ[c * 3 + 2] * d[2]);
+                    (r < 4 ? HqLo : HqHi)[2 * c * RecLayoutH::KS + 4 * r] = sq * (iJ[c * 3] * d[0] + iJ[c * 3 + 1] * d[1] + iJ[c * 3 + 2] * d[2]);
             });
 #pragma unroll
             for (int i = 0; i < 6; ++i) rec[RecLayoutH::OFF_S + 6 * gp + i] = -sq * sg[i];
@@ -469,7 +473,10 @@ __device__ __forceinline__ void elementTilesH(const double* T, int lane, bool wa
     Pr[0] = Pr[1] = Pr[2] = 0.0;
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
-        const double* S = T + H::OFF_S + 6 * (4 * ks + q);
+        // S'[gp][6]: 48 bytes per Gauss point, 16-byte aligned (OFF_S and PER_EL are even): three 128-bit loads
+        const double2* S2 = reinterpret_cast<const double2*>(T + H::OFF_S + 6 * (4 * ks + q));
+        const double2 s01 = S2[0], s23 = S2[1], s45 = S2[2];
+        const double S[6] = {s01.x, s01.y, s23.x, s23.y, s45.x, s45.y};
         Pr[0] += S[0] * h[ks][0] + S[3] * h[ks][1] + S[4] * h[ks][2];
         Pr[1] += S[3] * h[ks][0] + S[1] * h[ks][1] + S[5] * h[ks][2];
         Pr[2] += S[4] * h[ks][0] + S[5] * h[ks][1] + S[2] * h[ks][2];

@@ -14,7 +14,7 @@ def _select_kernel(monkeypatch, path):
     """The fused BoxGen kernel is chosen per material ('auto'); EWB_KERNEL (read at plan creation) forces one for every material:
     rowpipe = row-pipelined gather sweep with y-chaining (16 warps), rowpipe444 = the same without chaining (12 warps)."""
     if path == "rowpipe":
-        monkeypatch.setenv("EWB_KERNEL", "rpa4_8_4")
+        monkeypatch.setenv("EWB_KERNEL", "rpb4_8_4")
     elif path == "rowpipe444":
         monkeypatch.setenv("EWB_KERNEL", "rp4_4_4")
     else:
