@@ -93,7 +93,7 @@ struct RowPipeLayout {
 };
 
 // RP/RT/RG > 0: per-role register budgets (setmaxnreg, warp groups of four warps: NPW, NTW, NGW must be multiples of 4)
-template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0, int RECST = 2>
+template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0, int RECST = 2, bool USECHAIN = true>
 __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const SweepArgs A) {
     static_assert(RP == 0 || (NPW % 4 == 0 && NTW % 4 == 0 && NGW % 4 == 0), "setmaxnreg works on warp groups");
     // A P warp's consecutive tasks are NPW / HALVES rows apart and wait on the parity of a record stage only: the wait is
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
     // y-chaining: with one T warp per element position, the warp adds the previous element row's blocks of the shared y-face
     // to this row's (registers), so that the gather reads every (column, neighbour) pair from ONE element row.  Odd element
     // rows use the row index with the y bit inverted (flip), which puts the shared face at the same fragment positions.
-    constexpr bool CHAIN = (NTW == NE);
+    constexpr bool CHAIN = (NTW == NE) && USECHAIN;
 
     extern __shared__ double smem[];
     double* slots = smem + L::OFF_SLOTS;
@@ -638,7 +638,7 @@ inline RowPipeTiling rowPipeTiling(int64_t nX, int64_t nY, int64_t nZ, int nSM, 
     return best;
 }
 
-template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0, int RECST = 2>
+template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0, int RECST = 2, bool USECHAIN = true>
 int launchRowPipe(SweepPlan& sp, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st) {
     using L = RowPipeLayout<MC, TL, TZ, NPW, RECST>;
     constexpr int SMEM_MAX = 232448;
@@ -661,7 +661,7 @@ int launchRowPipe(SweepPlan& sp, const MatParams& mp, const ewb_buffers* b, int*
         a.timing = sp.timingBuf;
     }
 #endif
-    auto kern = rowPipeKernel<MC, TL, TZ, NPW, NTW, NGW, RP, RT, RG, RECST>;
+    auto kern = rowPipeKernel<MC, TL, TZ, NPW, NTW, NGW, RP, RT, RG, RECST, USECHAIN>;
     const size_t smem = ((size_t)L::fixedDoubles() + (size_t)L::carryDoubles(t.tileRows)) * sizeof(double);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EWB_ERR_CUDA;
     kern<<<(unsigned)grid, (NPW + NTW + NGW) * 32, smem, st>>>(a);
@@ -677,6 +677,8 @@ int launchRowPipeVariant(SweepPlan& sp, int variant, const MatParams& mp, const 
         case 30405: return launchRowPipe<MC, TL, 7, 3, 4, 5>(sp, mp, b, failFlag, flags, st);
         case 1040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120>(sp, mp, b, failFlag, flags, st);
         case 2040404: return launchRowPipe<MC, TL, 7, 4, 4, 4, 0, 0, 0, 3>(sp, mp, b, failFlag, flags, st);
+        case 8040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 152, 128, 104, 3, false>(sp, mp, b, failFlag, flags, st);
+        case 9040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 120, 104, 3, false>(sp, mp, b, failFlag, flags, st);
         case 5080404: return launchRowPipe<MC, TL, 7, 8, 4, 4, 152, 128, 80, 4>(sp, mp, b, failFlag, flags, st);
         case 7080404: return launchRowPipe<MC, TL, 7, 8, 4, 4, 144, 144, 80, 4>(sp, mp, b, failFlag, flags, st);
 #endif
