@@ -100,6 +100,12 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 #ifndef EWB_TILE_SYMMETRY
 #define EWB_TILE_SYMMETRY 0
 #endif
+// Residual row of the fragment-order (linear elastic) records on the tensor pipe; valid in the lanes with q == 0 (all callers use those).
+// Measured on B200 (round 2), parity green: row-pipelined kernel 647 -> 614 Melem/s (its tensor warps are FP64-pipe critical: +6 DMMA
+// cost more than 18 DFMA + 12 shuffles), first-generation sweep 551 -> 561.  Off by default; -DEWB_RESIDUAL_DMMA=1 enables it.
+#ifndef EWB_RESIDUAL_DMMA
+#define EWB_RESIDUAL_DMMA 0
+#endif
 __device__ __forceinline__ void mirrorTiles(double (&c)[3][3][2], int lane) {
     const int r = lane >> 2, q = lane & 3;
     const int src0 = 4 * (2 * q) + (r >> 1), src1 = src0 + 4;
@@ -471,8 +477,33 @@ __device__ __forceinline__ void elementTilesH(const double* T, int lane, bool wa
 #pragma unroll
         for (int j = 0; j < 3; ++j) c[i][j][0] = c[i][j][1] = 0.0;
     Pr[0] = Pr[1] = Pr[2] = 0.0;
+#if EWB_RESIDUAL_DMMA
+    // Residual row on the tensor pipe: P[a][i] = sum_{gp,j} h[a][(gp,j)] S'[(gp,j)][i] is an (8 x 24)(24 x 8) product, six m8n8k4 steps
+    // (k = Gauss points 4 ks + q of component j) whose A fragments are the h registers already loaded.  B fragment of this lane:
+    // column n = lane >> 2 (= residual component i, columns 3..7 are zero), k = q: the symmetric S'_ij of Gauss point 4 ks + q.
+    // Replaces 6 broadcast 128-bit loads (4 wavefronts each), 18 DFMA, 12 shuffles and 6 adds by 6 one-wavefront loads and 6 DMMA.
+    {
+        const int n = lane >> 2;
+        // Voigt index of S'_nj (11,22,33,12,13,23): n = 0: {0,3,4}, n = 1: {3,1,5}, n = 2: {4,5,2}
+        const int v0 = n == 0 ? 0 : (n == 1 ? 3 : 4), v1 = n == 0 ? 3 : (n == 1 ? 1 : 5), v2 = n == 0 ? 4 : (n == 1 ? 5 : 2);
+        double pacc[2] = {0.0, 0.0};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const double* S = T + H::OFF_S + 6 * (4 * ks + q);
+            const double b0 = n < 3 ? S[v0] : 0.0, b1 = n < 3 ? S[v1] : 0.0, b2 = n < 3 ? S[v2] : 0.0;
+            dmma(pacc, h[ks][0], b0);
+            dmma(pacc, h[ks][1], b1);
+            dmma(pacc, h[ks][2], b2);
+        }
+        // lane (row, q) holds columns 2q, 2q + 1: q = 0 -> P[a][0], P[a][1]; q = 1 -> P[a][2]; hand the third value to the q = 0 lane
+        Pr[0] = pacc[0];
+        Pr[1] = pacc[1];
+        Pr[2] = __shfl_down_sync(0xffffffffu, pacc[0], 1);
+    }
+#endif
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
+#if !EWB_RESIDUAL_DMMA
         // S'[gp][6]: 48 bytes per Gauss point, 16-byte aligned (OFF_S and PER_EL are even): three 128-bit loads
         const double2* S2 = reinterpret_cast<const double2*>(T + H::OFF_S + 6 * (4 * ks + q));
         const double2 s01 = S2[0], s23 = S2[1], s45 = S2[2];
@@ -480,6 +511,7 @@ __device__ __forceinline__ void elementTilesH(const double* T, int lane, bool wa
         Pr[0] += S[0] * h[ks][0] + S[3] * h[ks][1] + S[4] * h[ks][2];
         Pr[1] += S[3] * h[ks][0] + S[1] * h[ks][1] + S[5] * h[ks][2];
         Pr[2] += S[4] * h[ks][0] + S[5] * h[ks][1] + S[2] * h[ks][2];
+#endif
         if (wantK) {
 #pragma unroll
             for (int i = 0; i < 3; ++i)
@@ -488,11 +520,13 @@ __device__ __forceinline__ void elementTilesH(const double* T, int lane, bool wa
         }
     }
     if (EWB_TILE_SYMMETRY && wantK) mirrorTiles(c, lane);
+#if !EWB_RESIDUAL_DMMA
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         Pr[i] += __shfl_xor_sync(0xffffffffu, Pr[i], 1);
         Pr[i] += __shfl_xor_sync(0xffffffffu, Pr[i], 2);
     }
+#endif
 }
 
 // tangent assembly of node block t (0/1) of the lane from the raw accumulators: Kt[i*3+j] = Ke[3a+i][3b_t+j]
