@@ -272,12 +272,24 @@ class ElementAssembly:
         per-element layout) restores the stateless form: stateRef is uploaded before and stateTemp downloaded after the pass."""
         hU, hdU = self._pinned("U", self.nDof), self._pinned("dU", self.nDof)
         # U / dU None: the caller has filled the pinned input buffers of host_io() in place (no staging copy)
-        if U is not None:
+        if U is not None and dU is not None and self.nDof >= (1 << 20):
+            # two large pageable vectors: stage them on two threads (NumPy copies release the GIL) and start the first upload early
+            if getattr(self, "_stager", None) is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                self._stager = ThreadPoolExecutor(max_workers=1)
+            fut = self._stager.submit(np.copyto, hdU.numpy(), np.asarray(dU))
             hU.numpy()[:] = U
-        if dU is not None:
-            hdU.numpy()[:] = dU
-        self.U.copy_(hU, non_blocking=True)
-        self.dU.copy_(hdU, non_blocking=True)
+            self.U.copy_(hU, non_blocking=True)
+            fut.result()
+            self.dU.copy_(hdU, non_blocking=True)
+        else:
+            if U is not None:
+                hU.numpy()[:] = U
+            if dU is not None:
+                hdU.numpy()[:] = dU
+            self.U.copy_(hU, non_blocking=True)
+            self.dU.copy_(hdU, non_blocking=True)
         if stateRef_aos is not None:
             self.upload_state_ref(stateRef_aos)
         self.assemble(flags, time=time, dT=dT)

@@ -426,7 +426,9 @@ int ewb_plan_set_box(ewb_plan* p, int64_t nX, int64_t nY, int64_t nZ) {
         if (k == "v1") p->fusedVariant = 1;
         else if (k.rfind("rp", 0) == 0) {  // rp<P>_<T>_<G>
             int P = 4, T = 4, G = 4;
-            if (sscanf(k.c_str(), "rpn%d_%d_%d", &P, &T, &G) == 3) p->fusedVariant = 8000000 + 10000 * P + 100 * T + G;  // no chaining
+            if (sscanf(k.c_str(), "rph%d_%d_%d", &P, &T, &G) == 3) p->fusedVariant = 10000000 + 10000 * P + 100 * T + G;  // plain (J^-1) records
+            else if (sscanf(k.c_str(), "rpi%d_%d_%d", &P, &T, &G) == 3) p->fusedVariant = 11000000 + 10000 * P + 100 * T + G;
+            else if (sscanf(k.c_str(), "rpn%d_%d_%d", &P, &T, &G) == 3) p->fusedVariant = 8000000 + 10000 * P + 100 * T + G;  // no chaining
             else if (sscanf(k.c_str(), "rpm%d_%d_%d", &P, &T, &G) == 3) p->fusedVariant = 9000000 + 10000 * P + 100 * T + G;
             else if (sscanf(k.c_str(), "rpc%d_%d_%d", &P, &T, &G) == 3) p->fusedVariant = 5000000 + 10000 * P + 100 * T + G;
             else if (sscanf(k.c_str(), "rpd%d_%d_%d", &P, &T, &G) == 3) p->fusedVariant = 6000000 + 10000 * P + 100 * T + G;

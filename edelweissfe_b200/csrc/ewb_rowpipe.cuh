@@ -49,7 +49,7 @@ __device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity, volatil
     int spins = 0;
     while (!mbarTryWait(bar, parity)) {
         if (*abortFlag) return;
-        if (++spins > (1 << 17)) {
+        if (++spins > (1 << 22)) {
             *abortFlag = 1;
             atomicOr(failFlag, 4);
             return;
@@ -70,10 +70,10 @@ __device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity, volatil
 #define RP_FLUSH(cnt)
 #endif
 
-template <int MC, bool TL, int TZ, int NPW, int RECST = 2>
+template <int MC, bool TL, int TZ, int NPW, int RECST = 2, bool USEH = true>
 struct RowPipeLayout {
     static constexpr int NE = TZ + 1;  // elements per row (incl. halo)
-    static constexpr bool HREC = (MC == MC_LE) && !TL;
+    static constexpr bool HREC = (MC == MC_LE) && !TL && USEH;  // fragment-order records (the producers compute the scaled gradients)
     static constexpr int PEL = HREC ? RecLayoutH::PER_EL : RecLayout<MC>::PER_EL;
     static constexpr int SLOT_EL = 600;  // 576 stiffness-block doubles [lane][18] + 24 residual doubles [row][3]
     static constexpr int SLOT_STAGES = 3;
@@ -93,14 +93,14 @@ struct RowPipeLayout {
 };
 
 // RP/RT/RG > 0: per-role register budgets (setmaxnreg, warp groups of four warps: NPW, NTW, NGW must be multiples of 4)
-template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0, int RECST = 2, bool USECHAIN = true>
+template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0, int RECST = 2, bool USECHAIN = true, bool USEH = true>
 __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const SweepArgs A) {
     static_assert(RP == 0 || (NPW % 4 == 0 && NTW % 4 == 0 && NGW % 4 == 0), "setmaxnreg works on warp groups");
     // A P warp's consecutive tasks are NPW / HALVES rows apart and wait on the parity of a record stage only: the wait is
     // unambiguous as long as the warp cannot be two phases ahead of the T warps, i.e. row stride <= number of record stages.
     static_assert((NPW + (TZ + 1) / 4 - 1) / ((TZ + 1) / 4) <= RECST, "row stride of the producer warps must not exceed the record ring depth");
     constexpr int REG0 = (65536 / ((NPW + NTW + NGW) * 32)) / 8 * 8;  // registers per thread at launch
-    using L = RowPipeLayout<MC, TL, TZ, NPW, RECST>;
+    using L = RowPipeLayout<MC, TL, TZ, NPW, RECST, USEH>;
     using R = RecLayout<MC>;
     constexpr int NE = L::NE, PEL = L::PEL, SLOT_EL = L::SLOT_EL;
     constexpr bool HREC = L::HREC;
@@ -638,9 +638,9 @@ inline RowPipeTiling rowPipeTiling(int64_t nX, int64_t nY, int64_t nZ, int nSM, 
     return best;
 }
 
-template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0, int RECST = 2, bool USECHAIN = true>
+template <int MC, bool TL, int TZ, int NPW, int NTW, int NGW, int RP = 0, int RT = 0, int RG = 0, int RECST = 2, bool USECHAIN = true, bool USEH = true>
 int launchRowPipe(SweepPlan& sp, const MatParams& mp, const ewb_buffers* b, int* failFlag, int flags, cudaStream_t st) {
-    using L = RowPipeLayout<MC, TL, TZ, NPW, RECST>;
+    using L = RowPipeLayout<MC, TL, TZ, NPW, RECST, USEH>;
     constexpr int SMEM_MAX = 232448;
     const int rowsMax = (SMEM_MAX / 8 - L::fixedDoubles()) / (TZ * L::CARRY_COL);
     if (rowsMax < 1) return EWB_ERR_UNSUPPORTED;
@@ -661,7 +661,7 @@ int launchRowPipe(SweepPlan& sp, const MatParams& mp, const ewb_buffers* b, int*
         a.timing = sp.timingBuf;
     }
 #endif
-    auto kern = rowPipeKernel<MC, TL, TZ, NPW, NTW, NGW, RP, RT, RG, RECST, USECHAIN>;
+    auto kern = rowPipeKernel<MC, TL, TZ, NPW, NTW, NGW, RP, RT, RG, RECST, USECHAIN, USEH>;
     const size_t smem = ((size_t)L::fixedDoubles() + (size_t)L::carryDoubles(t.tileRows)) * sizeof(double);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return EWB_ERR_CUDA;
     kern<<<(unsigned)grid, (NPW + NTW + NGW) * 32, smem, st>>>(a);
@@ -677,6 +677,8 @@ int launchRowPipeVariant(SweepPlan& sp, int variant, const MatParams& mp, const 
         case 30405: return launchRowPipe<MC, TL, 7, 3, 4, 5>(sp, mp, b, failFlag, flags, st);
         case 1040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120>(sp, mp, b, failFlag, flags, st);
         case 2040404: return launchRowPipe<MC, TL, 7, 4, 4, 4, 0, 0, 0, 3>(sp, mp, b, failFlag, flags, st);
+        case 10040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 152, 128, 104, 3, true, false>(sp, mp, b, failFlag, flags, st);
+        case 11040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 144, 136, 96, 4, true, false>(sp, mp, b, failFlag, flags, st);
         case 8040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 152, 128, 104, 3, false>(sp, mp, b, failFlag, flags, st);
         case 9040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 120, 104, 3, false>(sp, mp, b, failFlag, flags, st);
         case 5080404: return launchRowPipe<MC, TL, 7, 8, 4, 4, 152, 128, 80, 4>(sp, mp, b, failFlag, flags, st);
