@@ -298,7 +298,11 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_bound = False
     if world > 1:
+        from edelweissfe_b200.partition import bind_to_gpu_numa
+
+        numa_bound = bind_to_gpu_numa(local_rank)  # before any pinned allocation: host buffers on the GPU's own socket
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -427,6 +431,8 @@ def main():
     }
     if plastic is not None:
         line["config"]["plastic_gauss_point_fraction"] = plastic
+    if world > 1:
+        line["config"]["host_placement"] = "ranks bound to their GPU's NUMA-local cores (NVML affinity)" if numa_bound else "default"
     if parity is not None:
         line["multi_gpu_parity"] = {"rel_err": parity, "what": "slab-partitioned vs single-GPU assembly of a small box (owned CSR rows, halo block, P, F), tol 1e-12"}
     if e2e:

@@ -28,6 +28,30 @@ from dataclasses import dataclass
 import numpy as np
 
 
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """Pin this process to the CPU cores that NVML reports as local to the GPU (same NUMA node / PCIe root), BEFORE pinned host
+    buffers are allocated: with one rank per GPU, every rank's host<->device traffic then stays on its own socket instead of
+    all ranks sharing one memory controller.  Returns False (and changes nothing) when NVML or the affinity call is unavailable."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:  # noqa: BLE001 - a placement hint only
+        return False
+
+
 def slab_ranges(nX: int, world: int):
     """Element-plane ranges [a_g, a_g+1) per rank, as even as possible."""
     base, rem = divmod(nX, world)
