@@ -17,7 +17,7 @@ from edelweissfe_b200 import ElementAssembly, box_mesh  # noqa: E402
 
 what = sys.argv[1] if len(sys.argv) > 1 else "le"
 variant = os.environ.get("EWB_KERNEL", "rp4_4_4")
-npw, ntw, ngw = (int(c) for c in variant.lstrip("rpsab").split("_"))
+npw, ntw, ngw = (int("".join(ch for ch in c if ch.isdigit())) for c in variant.split("_")[-3:])
 n = (100, 100, 100)
 coords, conn = box_mesh(*n, lX=100.0, lY=100.0, lZ=100.0)
 if what == "vm":
@@ -56,3 +56,11 @@ for name, a, b, labels in roles:
     cnt = w[:, :, 7].mean()
     print(f" role {name}: items per warp {cnt:.0f}; cycles per item: " + ", ".join(f"{lab} {w[:, :, i].mean() / cnt:.0f}" for i, lab in zip(range(6), labels) if lab != "-")
           + f"; total/item {w[:, :, 6].mean() / cnt:.0f}")
+
+if os.environ.get("EWB_TIMING_DETAIL"):
+    order = np.argsort(-tot)
+    print("slowest / fastest CTAs (index in launch order, total cycles; G-role: wait, lean loads, lean stores, general, residual):")
+    idx_all = np.nonzero(buf[:m].reshape(-1, NW, 8)[:, 0, 6] > 0)[0]
+    for k in list(order[:6]) + list(order[-4:]):
+        g = t[k, npw + ntw:, :].mean(axis=0)
+        print(f"  cta {idx_all[k]:4d} total {tot[k]:9.0f}  rows {t[k, -1, 7]:5.0f}  G per row: wait {g[0] / g[7]:6.0f} loads {g[1] / g[7]:6.0f} stores {g[2] / g[7]:6.0f} general {g[3] / g[7]:6.0f} resid {g[4] / g[7]:6.0f}")
