@@ -36,6 +36,16 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / scale)
 
 
+def entrywise(a, b, rel=1e-9, floor=1e-13):
+    """Entry-wise check next to the norm-wise relerr: max over entries of |a - b| / (rel |b| + floor max|b|); <= 1 passes.
+    A small-magnitude block that is wrong by O(1) relative fails here even when max-abs / max-abs is tiny."""
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    if b.size == 0:
+        return 0.0
+    return float((np.abs(a - b) / (rel * np.abs(b) + floor * np.abs(b).max() + 1e-300)).max())
+
+
 @pytest.fixture(scope="session")
 def has_cuda():
     import torch

@@ -5,16 +5,9 @@ the same U, dU and state; compared ENTRY-WISE (relative with an absolute floor, 
 nodes whose elements all lie inside the block, their P and F, and the updated state of every element of the block."""
 import numpy as np
 import pytest
-from conftest import relerr
+from conftest import entrywise, relerr
 
 pytestmark = pytest.mark.gpu
-
-
-def entrywise(a, b, rel=1e-9, floor=1e-13):
-    """max over entries of |a - b| / (rel |b| + floor max|b|) — <= 1 passes."""
-    a = np.asarray(a, dtype=float)
-    b = np.asarray(b, dtype=float)
-    return float((np.abs(a - b) / (rel * np.abs(b) + floor * np.abs(b).max() + 1e-300)).max())
 
 
 def _blocks(n, bs):

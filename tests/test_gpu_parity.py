@@ -3,7 +3,7 @@ and against the oracle on seeded inputs.  Tolerance: 1e-12 relative (max-abs / m
 state (north_star); CSR pattern, slot map and dof indexing bit-exact."""
 import numpy as np
 import pytest
-from conftest import golden_names, load_golden, relerr
+from conftest import entrywise, golden_names, load_golden, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -120,6 +120,10 @@ def test_against_oracle_seeded(elType, material, props, n, scale, path, monkeypa
         assert relerr(asm.P.cpu().numpy(), o["P"]) < TOL
         assert relerr(asm.F.cpu().numpy(), o["F"]) < TOL
         assert relerr(asm.state_aos("temp").cpu().numpy(), o["stateTemp"]) < TOL
+        # entry-wise as well (relative 1e-9 with an absolute floor of 1e-13 of the largest entry)
+        assert entrywise(asm.csr_data.cpu().numpy(), o["data"]) <= 1.0
+        assert entrywise(asm.F.cpu().numpy(), o["F"]) <= 1.0
+        assert entrywise(asm.state_aos("temp").cpu().numpy(), o["stateTemp"]) <= 1.0
         asm.accept_last_state()
         state = o["stateTemp"]
 
