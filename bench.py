@@ -223,7 +223,7 @@ def roofline_of(workload, elType, material, asm, ms_per_step, fused, plastic_fra
     return {"bound": "hbm" if achieved / peak >= tf / fpeak else "fp64", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": measured_traffic(workload, path), "peak_source": peak_src, "algorithmic_bytes_per_element": balg,
             "fp64": {"achieved": tf, "peak": fpeak, "unit": "TFLOP/s", "frac": tf / fpeak, "algorithmic_flops_per_element": falg, "peak_source": fpeak_src},
-            "kernel": ("rowPipeKernel (row-pipelined gather sweep)" if material == "linearelastic" else "sweepKernel") + " (1 launch = 1 step)" if fused
+            "kernel": "rowPipeKernel (row-pipelined gather sweep; 1 launch = 1 step)" if fused
             else "computeElementsVij+gatherResidual+rowGatherHalf (3 launches = 1 step)"}
 
 

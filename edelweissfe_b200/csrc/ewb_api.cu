@@ -499,9 +499,10 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
 
     if (p->isBox && !(flags & EWB_FLAG_FORCE_GENERIC) && b->vij == nullptr) {
         if (!p->sweep.indexable()) return fail(EWB_ERR_UNSUPPORTED, "ewb_assemble: the fused BoxGen kernels index nodes with int32 (3 * nodes < 2^31); use EWB_FLAG_FORCE_GENERIC");
-        // automatic choice (B200, round 2): linear elasticity runs the row-pipelined kernel (598 vs 551 Melem/s at 100^3); von Mises and
-        // Neo-Hooke, whose phase A is heavier than four producer warps can feed, stay on the first-generation sweep (334 vs 307, 413 vs 352)
-        const int variant = p->fusedVariant != 0 ? p->fusedVariant : (mc == ewb::MC_LE ? 4040804 : 1);
+        // automatic choice (B200, round 2, Melem/s at the BASELINE sizes): the row-pipelined kernel for every material — linear elasticity with
+        // y-chaining (648 vs 551 for the first-generation sweep), von Mises without chaining and with the tile-transpose identity (360 vs 333),
+        // Neo-Hooke without chaining (442 vs 413); the role register budgets differ (P / T / G: 152/128/104, 152/136/88, 144/136/96)
+        const int variant = p->fusedVariant != 0 ? p->fusedVariant : (mc == ewb::MC_LE ? 4040804 : (mc == ewb::MC_VM ? 9040804 : 8040804));
         const bool v1 = (flags & EWB_FLAG_SWEEP_V1) || variant == 1;
         const int rc = v1 ? p->sweep.launchV1(p->elType, mc, mp, b, p->failFlag, flags, st)
                           : ewb::launchRowPipeAny(p->sweep, variant, p->elType, mc, mp, b, p->failFlag, flags, st);

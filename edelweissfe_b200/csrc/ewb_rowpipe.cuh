@@ -290,7 +290,7 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
                     const double* T = records + (size_t)(rs * NE + k) * PEL;
                     TileAcc<MC> acc;
                     if constexpr (HREC) elementTilesH(T, lane, wantK, acc, Pr);
-                    else elementTiles<MC>(T, lane, dNl, A.mp, wantK, acc, Pr);
+                    else elementTiles<MC, MC == MC_VM>(T, lane, dNl, A.mp, wantK, acc, Pr);
                     finishBlock<MC>(acc, 0, A.mp, Kc0);
                     finishBlock<MC>(acc, 1, A.mp, Kc1);
                     if constexpr (CHAIN) {
@@ -337,13 +337,19 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
             RP_LAP(3);
             if (++jj == rowsPerStep) jj = 0;
         };
-        double Ka0[9], Ka1[9], Kb0[9], Kb1[9];
+        if constexpr (CHAIN) {
+            double Ka0[9], Ka1[9], Kb0[9], Kb1[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) Ka0[i] = Ka1[i] = Kb0[i] = Kb1[i] = 0.0;
+            for (int i = 0; i < 9; ++i) Ka0[i] = Ka1[i] = Kb0[i] = Kb1[i] = 0.0;
 #pragma unroll 1
-        for (int n = 0; n < nRows; n += 2) {
-            row(n, Ka0, Ka1, Kb0, Kb1);
-            if (n + 1 < nRows) row(n + 1, Kb0, Kb1, Ka0, Ka1);
+            for (int n = 0; n < nRows; n += 2) {
+                row(n, Ka0, Ka1, Kb0, Kb1);
+                if (n + 1 < nRows) row(n + 1, Kb0, Kb1, Ka0, Ka1);
+            }
+        } else {
+            double Ka0[9], Ka1[9];  // no chaining: one block set
+#pragma unroll 1
+            for (int n = 0; n < nRows; ++n) row(n, Ka0, Ka1, Ka0, Ka1);
         }
         RP_FLUSH(nRows);
         return;
@@ -679,12 +685,12 @@ int launchRowPipeVariant(SweepPlan& sp, int variant, const MatParams& mp, const 
         case 2040404: return launchRowPipe<MC, TL, 7, 4, 4, 4, 0, 0, 0, 3>(sp, mp, b, failFlag, flags, st);
         case 10040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 152, 128, 104, 3, true, false>(sp, mp, b, failFlag, flags, st);
         case 11040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 144, 136, 96, 4, true, false>(sp, mp, b, failFlag, flags, st);
-        case 8040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 152, 128, 104, 3, false>(sp, mp, b, failFlag, flags, st);
-        case 9040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 120, 104, 3, false>(sp, mp, b, failFlag, flags, st);
         case 5080404: return launchRowPipe<MC, TL, 7, 8, 4, 4, 152, 128, 80, 4>(sp, mp, b, failFlag, flags, st);
         case 7080404: return launchRowPipe<MC, TL, 7, 8, 4, 4, 144, 144, 80, 4>(sp, mp, b, failFlag, flags, st);
 #endif
         case 40404: return launchRowPipe<MC, TL, 7, 4, 4, 4>(sp, mp, b, failFlag, flags, st);
+        case 8040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 144, 136, 96, 3, false>(sp, mp, b, failFlag, flags, st);  // no chaining (von Mises / Neo-Hooke)
+        case 9040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 152, 136, 88, 3, false>(sp, mp, b, failFlag, flags, st);
 #ifdef EWB_VARIANTS
         case 2040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 112, 120, 3>(sp, mp, b, failFlag, flags, st);
         case 3040804: return launchRowPipe<MC, TL, 7, 4, 8, 4, 168, 120, 104, 3>(sp, mp, b, failFlag, flags, st);
