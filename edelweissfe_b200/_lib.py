@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("EWB_LIB_PATH", os.path.join(_HERE, "libedelweiss_b200
 EWB_C3D8, EWB_C3D20, EWB_C3D8TL, EWB_C3D8R, EWB_C3D8E, EWB_C3D20R = 0, 1, 2, 3, 4, 5
 EWB_MAT_LINEARELASTIC, EWB_MAT_VONMISES, EWB_MAT_NEOHOOKE_WA, EWB_MAT_NEOHOOKE_WB, EWB_MAT_NEOHOOKE_WC = 0, 1, 2, 3, 4
 EWB_OK, EWB_CUTBACK = 0, 1
-EWB_FLAG_ACCUMULATE_PF, EWB_FLAG_FORCE_GENERIC, EWB_FLAG_NO_STIFFNESS, EWB_FLAG_SWEEP_V1 = 1, 2, 4, 8
+EWB_FLAG_ACCUMULATE_PF, EWB_FLAG_FORCE_GENERIC, EWB_FLAG_NO_STIFFNESS, EWB_FLAG_SWEEP_V1, EWB_FLAG_TWO_PHASE = 1, 2, 4, 8, 16
 
 ELEMENT_CODES = {"C3D8": EWB_C3D8, "C3D8N": EWB_C3D8, "C3D20": EWB_C3D20, "C3D20N": EWB_C3D20, "C3D8TL": EWB_C3D8TL, "C3D8NTL": EWB_C3D8TL,
                  "C3D8R": EWB_C3D8R, "C3D8E": EWB_C3D8E, "C3D20R": EWB_C3D20R}
@@ -63,6 +63,7 @@ SYMBOLS = {
     "ewb_plan_set_box": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64]),
     "ewb_plan_is_box": (C.c_int, [_P]),
     "ewb_plan_set_gather_order": (C.c_int, [_P, _P]),
+    "ewb_plan_set_element_order": (C.c_int, [_P, _P]),
     "ewb_assemble": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(EwbBuffers), C.POINTER(C.c_double), C.c_double, C.c_int, _P]),
     "ewb_poll_status": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
     "ewb_compute_elements_vij": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(EwbBuffers), _P, C.c_int, _P]),

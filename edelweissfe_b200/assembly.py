@@ -87,6 +87,12 @@ class ElementAssembly:
         if os.environ.get("EWB_GATHER_ORDER", "none") == "morton":
             order = morton_order(coords_t.detach().cpu().numpy())
             check(self.lib.ewb_plan_set_gather_order(self.plan, order.ctypes.data_as(C.c_void_p)))
+        # task-stream kernel for 20-node hexahedra (opt-in, EWB_STREAM=1): elements are processed along a Morton curve of their
+        # centroids, so that a node's CSR rows are gathered soon after the matrices of its elements were written (locality hint,
+        # results unchanged)
+        if self.nn == 20 and os.environ.get("EWB_STREAM", "0") == "1" and os.environ.get("EWB_ELEMENT_ORDER", "morton") == "morton":
+            cen = coords_t.detach().cpu().numpy()[conn.astype(np.int64)].mean(axis=1)
+            check(self.lib.ewb_plan_set_element_order(self.plan, morton_order(cen).ctypes.data_as(C.c_void_p)))
         self.nnz = self.lib.ewb_plan_nnz(self.plan)
         f64 = dict(dtype=torch.float64, device=self.device)
         self.coords = coords_t.to(**f64).contiguous()
@@ -302,6 +308,47 @@ class ElementAssembly:
         if stateTemp_aos is not None:
             np.asarray(stateTemp_aos).reshape(-1)[:] = self._pinned("S", self.nEl * self.nGp * self.nState).numpy()
         return hP.numpy(), hF.numpy()  # views of the pinned output buffers: valid until the next call
+
+    # ---- the lean per-iteration call: U_n device resident, dU in, P and the flux norm out --------------------------------------
+    def begin_increment(self, U_n=None):
+        """U_n of the increment that starts (first argument of NIST.solveIncrement, nonlinearimplicitstatic.py:334-347) becomes
+        device resident: every Newton iteration of the increment then uploads dU only and forms U_np = U_n + dU on the device —
+        the same IEEE addition the solver does on the host (:416-417), bit for bit.  None: the pinned U buffer of host_io() was
+        filled in place."""
+        if getattr(self, "Un", None) is None:
+            self.Un = torch.zeros(self.nDof, dtype=torch.float64, device=self.device)
+            self._fsum = torch.zeros(1, dtype=torch.float64, device=self.device)
+            self._pin_fsum = torch.zeros(1, dtype=torch.float64).pin_memory()
+        hU = self._pinned("U", self.nDof)
+        if U_n is not None:
+            hU.numpy()[:] = U_n
+        self.Un.copy_(hU, non_blocking=True)
+
+    def _increment_upload(self, dU):
+        hdU = self._pinned("dU", self.nDof)
+        if dU is not None:
+            hdU.numpy()[:] = dU
+        self.dU.copy_(hdU, non_blocking=True)
+        torch.add(self.Un, self.dU, out=self.U)
+
+    def _increment_download(self, n_owned=None):
+        hP = self._pinned("P", self.nDof)
+        hP.copy_(self.P, non_blocking=True)
+        F = self.F if n_owned is None else self.F[:n_owned]
+        torch.sum(F, dim=0, keepdim=True, out=self._fsum)  # F >= 0: the 1-norm checkConvergence needs (:785-790)
+        self._pin_fsum.copy_(self._fsum, non_blocking=True)
+        return hP
+
+    def compute_host_increment(self, dU, time=(0.0, 0.0), dT=0.0, flags=0):
+        """One Newton iteration of the current increment with HOST dU (after begin_increment): returns (P, sum|F|).  P is a view of
+        a pinned buffer (valid until the next call); F itself stays on the device (self.F) — the solver only ever takes its 1-norm
+        per field (computeSpatialAveragedFluxes, :771-792).  Per iteration one dof vector crosses PCIe in each direction.
+        Raises CutbackRequest."""
+        self._increment_upload(dU)
+        self.assemble(flags, time=time, dT=dT)
+        hP = self._increment_download()
+        self.poll()
+        return hP.numpy(), float(self._pin_fsum[0])
 
     def host_io(self):
         """Pinned host buffers of compute_host as NumPy views: (U, dU) inputs a caller may fill in place, (P, F) outputs."""

@@ -16,6 +16,7 @@
 #include "ewb_sweep.cuh"
 #include "ewb_rowpipe.cuh"
 #include "ewb_solver.cuh"
+#include "ewb_stream.cuh"
 
 namespace {
 
@@ -109,6 +110,20 @@ struct ewb_plan {
     int64_t nX = 0, nY = 0, nZ = 0;
     std::vector<int32_t> connHost;
     ewb::SweepPlan sweep;
+    // task-stream kernel of the arbitrary-mesh path (ewb_stream.cuh): schedule built at first use
+    std::vector<int32_t> elOrderHost;  // optional element processing order (ewb_plan_set_element_order)
+    bool streamBuilt = false;
+    int2* streamTasks = nullptr;
+    int streamNTasks = 0, streamNChunks = 0;
+    int32_t* streamElOrder = nullptr;
+    int32_t* streamGatherNodes = nullptr;
+    int32_t* streamChunkTarget = nullptr;
+    int* streamSync = nullptr;
+    double* streamRows = nullptr;
+    int streamDiscard = 1;   // EWB_STREAM_DISCARD, read once at plan creation
+    int streamEnabled = 0;   // EWB_STREAM=1 selects the task-stream kernel for 20-node hexahedra (read once at plan creation)
+    int streamChunk = 256, streamDelay = 12, streamElPerTask = 2, streamNodesPerTask = 8;  // EWB_STREAM_CHUNK / _DELAY / _EPT / _NPT
+    int streamCtasPerSm = 0;  // EWB_STREAM_CTAS: cap of resident CTAs per SM (0 = occupancy limit)
     int fusedVariant = 0;  // 0 = automatic (measured best per material); 1 = first-generation sweep; else row-pipelined kernel variant (EWB_KERNEL, read once at plan creation)
 };
 
@@ -187,6 +202,138 @@ int dispatchVij(ewb_plan* p, int mc, const ewb::MatParams& mp, const ewb_buffers
         if (mc == ewb::MC_VM) return launchVij<20, 8, ewb::MC_VM, false, 32, 4, 4>(p, mp, b, V, Pe, st, halfScratch);
     }
     return fail(EWB_ERR_UNSUPPORTED, "element/material combination not implemented");
+}
+
+// ---- task-stream kernel (ewb_stream.cuh): schedule ------------------------------------------------------------------------
+// Element positions (the processing order) are cut into chunks of CE; a node is ready when the last chunk holding one of its
+// incident elements is complete.  Ticket order: element tasks of chunk c, then the gather tasks of the nodes that became ready
+// with chunk c - D.  Every gather task therefore depends only on tasks with a lower ticket.
+void streamRelease(ewb_plan* p) {
+    cudaFree(p->streamTasks); cudaFree(p->streamElOrder); cudaFree(p->streamGatherNodes); cudaFree(p->streamChunkTarget); cudaFree(p->streamSync);
+    p->streamTasks = nullptr; p->streamElOrder = nullptr; p->streamGatherNodes = nullptr; p->streamChunkTarget = nullptr; p->streamSync = nullptr;
+    p->streamBuilt = false;
+}
+
+int streamBuild(ewb_plan* p) {
+    streamRelease(p);
+    const int64_t nEl = p->nEl, nNode = p->nNode;
+    const int nn = p->nn;
+    const int64_t CE = p->streamChunk;
+    const int EPT = p->streamElPerTask, NPT = p->streamNodesPerTask, D = p->streamDelay;
+    const int64_t nChunks = (nEl + CE - 1) / CE;
+    if (nChunks >= (1 << 22)) return fail(EWB_ERR_UNSUPPORTED, "stream schedule: too many chunks");
+    const bool ordered = !p->elOrderHost.empty();
+    // chunk of every element
+    std::vector<int32_t> chunkOf((size_t)nEl);
+    for (int64_t pos = 0; pos < nEl; ++pos) chunkOf[ordered ? p->elOrderHost[pos] : pos] = (int32_t)(pos / CE);
+    // ready chunk of every node (nodes without elements: chunk 0)
+    std::vector<int32_t> ready((size_t)nNode, 0);
+    for (int64_t e = 0; e < nEl; ++e)
+        for (int a = 0; a < nn; ++a) {
+            int32_t& r = ready[p->connHost[e * nn + a]];
+            r = std::max(r, chunkOf[e]);
+        }
+    // nodes by ready chunk, ascending node inside a chunk (counting sort)
+    std::vector<int64_t> gPtr((size_t)nChunks + 1, 0);
+    for (int64_t n = 0; n < nNode; ++n) gPtr[ready[n] + 1]++;
+    for (int64_t c = 0; c < nChunks; ++c) gPtr[c + 1] += gPtr[c];
+    std::vector<int32_t> gatherNodes((size_t)nNode);
+    {
+        std::vector<int64_t> cur(gPtr.begin(), gPtr.end() - 1);
+        for (int64_t n = 0; n < nNode; ++n) gatherNodes[cur[ready[n]]++] = (int32_t)n;
+    }
+    std::vector<int2> tasks;
+    tasks.reserve((size_t)(nEl / EPT + nNode / NPT + 2 * nChunks + 16));
+    std::vector<int32_t> target((size_t)nChunks, 0);
+    auto pushGather = [&](int64_t c) {
+        for (int64_t g = gPtr[c]; g < gPtr[c + 1]; g += NPT) {
+            const int cnt = (int)std::min<int64_t>(NPT, gPtr[c + 1] - g);
+            tasks.push_back(make_int2((int)((c << 8) | (cnt << 1) | 1), (int)g));
+        }
+    };
+    for (int64_t c = 0; c < nChunks; ++c) {
+        const int64_t p0 = c * CE, p1 = std::min(nEl, p0 + CE);
+        for (int64_t q = p0; q < p1; q += EPT) {
+            const int cnt = (int)std::min<int64_t>(EPT, p1 - q);
+            tasks.push_back(make_int2((int)((c << 8) | (cnt << 1)), (int)q));
+            target[c]++;
+        }
+        if (c - D >= 0) pushGather(c - D);
+    }
+    for (int64_t c = std::max<int64_t>(0, nChunks - D); c < nChunks; ++c) pushGather(c);
+    if (tasks.size() >= ((size_t)1 << 30)) return fail(EWB_ERR_UNSUPPORTED, "stream schedule: too many tasks");
+    p->streamNTasks = (int)tasks.size();
+    p->streamNChunks = (int)nChunks;
+    int rc = EWB_OK;
+    if ((rc = upload(&p->streamTasks, tasks)) || (rc = upload(&p->streamGatherNodes, gatherNodes)) || (rc = upload(&p->streamChunkTarget, target))) return rc;
+    if (ordered && (rc = upload(&p->streamElOrder, p->elOrderHost))) return rc;
+    CUDA_TRY(cudaMalloc((void**)&p->streamSync, (size_t)(nChunks + 2) * sizeof(int)));
+    p->streamBuilt = true;
+    return EWB_OK;
+}
+
+template <int NGP, int MC, int MINB>
+int streamLaunchT(ewb_plan* p, const ewb::StreamArgs& a, const ewb::MatParams& mp, cudaStream_t st) {
+    constexpr int WARPS = 4;
+    using L = ewb::TileLayout<20, NGP, MC>;
+    int stride = std::max<int>(L::PER_EL, 9 * p->maxDeg);
+    stride += ((8 - stride % 16) + 16) % 16;  // == 8 (mod 16) doubles, like TileLayout::PER_EL (bank spread of the warps' images)
+    const size_t smem = (size_t)WARPS * stride * sizeof(double);
+    auto kern = ewb::streamKernel<20, NGP, MC, WARPS, MINB>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int perSm = 0, nSm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, WARPS * 32, smem));
+    CUDA_TRY(cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, p->device));
+    if (perSm < 1) return fail(EWB_ERR_CUDA, "stream kernel does not fit on an SM");
+    const int64_t want = ((int64_t)a.nTasks + WARPS - 1) / WARPS;
+    if (p->streamCtasPerSm > 0) perSm = std::min(perSm, p->streamCtasPerSm);
+    const unsigned grid = (unsigned)std::min<int64_t>((int64_t)perSm * nSm, std::max<int64_t>(want, 1));
+    CUDA_TRY(cudaMemsetAsync(p->streamSync, 0, (size_t)(p->streamNChunks + 2) * sizeof(int), st));
+    kern<<<grid, WARPS * 32, smem, st>>>(a, mp, stride);
+    LAUNCH_CHECK();
+    return EWB_OK;
+}
+
+// ewb_assemble for 20-node hexahedra on the task-stream kernel; EWB_ERR_UNSUPPORTED = use the two-phase path
+int streamAssemble(ewb_plan* p, int mc, const ewb::MatParams& mp, const ewb_buffers* b, int flags, cudaStream_t st) {
+    if (p->nn != 20 || !p->streamEnabled || p->maxDeg > 255) return EWB_ERR_UNSUPPORTED;
+    if (mc != ewb::MC_LE && mc != ewb::MC_VM) return EWB_ERR_UNSUPPORTED;
+    if (!p->streamBuilt)
+        if (int rc = streamBuild(p)) return rc;
+    using RL = ewb::RowLayout<20>;
+    if (!p->streamRows) CUDA_TRY(cudaMalloc((void**)&p->streamRows, (size_t)p->nEl * RL::SE * sizeof(double)));
+    if (!p->gatherSlots) {
+        const int64_t nInc = p->nEl * p->nn;
+        CUDA_TRY(cudaMalloc((void**)&p->gatherSlots, (size_t)nInc * p->nn));
+        const unsigned g = (unsigned)((p->nNode + 7) / 8);
+        ewb::gatherSlotKernel<20><<<g, 256, 0, st>>>(p->nNode, p->adjPtr, p->adj, p->incPtr, p->inc, p->conn, p->gatherSlots);
+        LAUNCH_CHECK();
+    }
+    ewb::StreamArgs a;
+    a.nEl = p->nEl; a.nNode = p->nNode; a.conn = p->conn; a.coords = b->coords; a.U = b->U; a.dU = b->dU;
+    a.stateRef = b->state_ref; a.stateTemp = b->state_temp; a.rows = p->streamRows;
+    a.adjPtr = p->adjPtr; a.incPtr = p->incPtr; a.inc = p->inc; a.slotTab = p->gatherSlots;
+    a.data = b->csr_data; a.P = b->P; a.F = b->F;
+    a.tasks = p->streamTasks; a.nTasks = p->streamNTasks; a.elOrder = p->streamElOrder; a.gatherNodes = p->streamGatherNodes;
+    a.chunkTarget = p->streamChunkTarget; a.nChunks = p->streamNChunks; a.sync = p->streamSync; a.failFlag = p->failFlag;
+    a.accumulate = (flags & EWB_FLAG_ACCUMULATE_PF) ? 1 : 0;
+    a.discard = p->streamDiscard;
+    a.wantK = (flags & EWB_FLAG_NO_STIFFNESS) ? 0 : 1;
+    if (p->ngp == 27) {
+        if (mc == ewb::MC_LE) return streamLaunchT<27, ewb::MC_LE, 3>(p, a, mp, st);
+        return streamLaunchT<27, ewb::MC_VM, 1>(p, a, mp, st);
+    }
+    if (p->ngp == 8) {
+        if (mc == ewb::MC_LE) return streamLaunchT<8, ewb::MC_LE, 3>(p, a, mp, st);
+        return streamLaunchT<8, ewb::MC_VM, 2>(p, a, mp, st);
+    }
+    return EWB_ERR_UNSUPPORTED;
+}
+
+int envInt(const char* name, int dflt, int lo, int hi) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return std::min(hi, std::max(lo, atoi(v)));
 }
 
 }  // namespace
@@ -274,6 +421,14 @@ int ewb_plan_create(ewb_plan** out, int el_type, int64_t n_el, int64_t n_node, c
         }
     }
     *p->failHost = 0;
+    // tuning / A-B knobs of the task-stream kernel, read once
+    p->streamEnabled = envInt("EWB_STREAM", 0, 0, 1);  // measured slower than the two-phase path on B200: opt-in
+    p->streamDiscard = envInt("EWB_STREAM_DISCARD", 1, 0, 1);
+    p->streamChunk = envInt("EWB_STREAM_CHUNK", 256, 1, 1 << 20);
+    p->streamDelay = envInt("EWB_STREAM_DELAY", 12, 0, 1 << 10);
+    p->streamElPerTask = envInt("EWB_STREAM_EPT", 2, 1, 127);
+    p->streamNodesPerTask = envInt("EWB_STREAM_NPT", 8, 1, 32);
+    p->streamCtasPerSm = envInt("EWB_STREAM_CTAS", 0, 0, 32);
     *out = p;
     return EWB_OK;
 }
@@ -287,6 +442,8 @@ void ewb_plan_destroy(ewb_plan* p) {
     if (p->pcgScalHost) cudaFreeHost(p->pcgScalHost);
     if (p->failHost) cudaFreeHost(p->failHost);
     p->sweep.release();
+    streamRelease(p);
+    cudaFree(p->streamRows);
     delete p;
 }
 
@@ -462,6 +619,24 @@ int ewb_plan_set_gather_order(ewb_plan* p, const int32_t* order_host) {
     return EWB_OK;
 }
 
+int ewb_plan_set_element_order(ewb_plan* p, const int32_t* order_host) {
+    if (!p) return fail(EWB_ERR_ARG, "null plan");
+    WITH_DEVICE(p->device);
+    if (order_host) {
+        std::vector<char> seen((size_t)p->nEl, 0);
+        for (int64_t i = 0; i < p->nEl; ++i) {
+            const int32_t v = order_host[i];
+            if (v < 0 || v >= p->nEl || seen[v]) return fail(EWB_ERR_ARG, "ewb_plan_set_element_order: not a permutation of the elements");
+            seen[v] = 1;
+        }
+        p->elOrderHost.assign(order_host, order_host + p->nEl);
+    } else {
+        p->elOrderHost.clear();
+    }
+    streamRelease(p);  // rebuilt at the next assembly
+    return EWB_OK;
+}
+
 int ewb_compute_elements_vij(ewb_plan* p, int material, const double* props, int n_props, const ewb_buffers* b, double* pe_dev, int flags,
                              void* stream) {
     if (!p || !b || !props || !pe_dev) return fail(EWB_ERR_ARG, "ewb_compute_elements_vij: bad arguments");
@@ -513,8 +688,13 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
         if (rc != EWB_ERR_UNSUPPORTED) return fail(rc, std::string("fused sweep launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     }
 
-    // generic two-phase path
     if (p->sweep.peerData) return fail(EWB_ERR_UNSUPPORTED, "ewb_assemble: peer interface buffers need the fused sweep path");
+    // 20-node hexahedra: element loop and row gather as warp tasks of one persistent kernel (ewb_stream.cuh)
+    if (b->vij == nullptr && !(flags & EWB_FLAG_TWO_PHASE)) {
+        const int rc = streamAssemble(p, mc, mp, b, flags, st);
+        if (rc != EWB_ERR_UNSUPPORTED) return rc;
+    }
+    // generic two-phase path
     const int nd = 3 * p->nn;
     if (!p->peScratch) CUDA_TRY(cudaMalloc((void**)&p->peScratch, (size_t)p->nEl * nd * sizeof(double)));
     double* V = nullptr;

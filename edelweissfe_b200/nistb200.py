@@ -154,7 +154,9 @@ def make_solver_class(backend_factory=default_backend):
     class NISTB200(NIST):
         identification = "NISTB200Solver"
         # b200solver: "host" = scipy CSR for the reference's linsolver (default), "pcg" = matrix stays on the device (Jacobi-PCG)
-        NISTOptions = dict(NIST.NISTOptions, b200solver="host", b200pcgtol=1e-12, b200pcgmaxiter=100000)
+        # b200io: "lean" = U_n device resident per increment, per Newton iteration dU in and P + the flux 1-norm out (one dof vector each
+        #         way); "full" = U_np, dU in and P, F out, the literal signature of NIST.computeElements
+        NISTOptions = dict(NIST.NISTOptions, b200solver="host", b200pcgtol=1e-12, b200pcgmaxiter=100000, b200io="lean")
 
         def _b200_setup(self, elements):
             self._b200_dm = self.theDofManager
@@ -185,21 +187,54 @@ def make_solver_class(backend_factory=default_backend):
             finally:
                 del model.advanceToTime
 
+        def solveIncrement(self, U_n, dU, P, K, stepActions, model, timeStep, prevTimeStep, extrapolation, maxIter, maxGrowingIter):
+            """NIST.solveIncrement (:334-456); remembers U_n so that the element loop can keep it on the device for the whole increment."""
+            self._b200_Un = U_n
+            self._b200_Un_sent = False
+            self._b200_flux = None
+            try:
+                return super().solveIncrement(U_n, dU, P, K, stepActions, model, timeStep, prevTimeStep, extrapolation, maxIter, maxGrowingIter)
+            finally:
+                self._b200_Un = None
+
         def computeElements(self, elements, U_np, dU, P, K, F, timeStep):
             tic = _time.time()
             if getattr(self, "_b200_dm", None) is not self.theDofManager:
                 self._b200_setup(elements)
             asm = self._b200_asm
+            lean = str(self.options.get("b200io", "lean")).lower() == "lean" and getattr(self, "_b200_Un", None) is not None \
+                and hasattr(asm, "compute_host_increment")
+            tm = dict(time=(timeStep.stepTime, timeStep.totalTime), dT=timeStep.timeIncrement)
             try:
-                Pel, Fel = asm.compute_host(np.asarray(U_np), np.asarray(dU), time=(timeStep.stepTime, timeStep.totalTime), dT=timeStep.timeIncrement)
+                if lean:
+                    if not self._b200_Un_sent:
+                        asm.begin_increment(np.asarray(self._b200_Un))
+                        self._b200_Un_sent = True
+                    Pel, self._b200_flux = asm.compute_host_increment(np.asarray(dU), **tm)  # U_np = U_n + dU on the device (:416-417)
+                else:
+                    Pel, Fel = asm.compute_host(np.asarray(U_np), np.asarray(dU), **tm)
+                    self._b200_flux = None
             except Exception as e:  # device-side material failure -> the reference's cut-back request
                 if type(e).__name__ == "CutbackRequest":
                     raise CutbackRequest(str(e), e.cutbackSize)
                 raise
             P += Pel  # P[el] += Pe for all elements (:843)
-            F += Fel  # F[el] += abs(Pe)            (:844)
+            if not lean:
+                F += Fel  # F[el] += abs(Pe)            (:844)
             self.computationTimes["elements"] += _time.time() - tic
             return P, K, F
+
+        def computeSpatialAveragedFluxes(self, F):
+            """:771-792.  In lean mode the element fluxes were summed on the device (F >= 0, so the sum is the 1-norm); whatever else
+            the host vector F holds is added to it."""
+            flux = getattr(self, "_b200_flux", None)
+            if flux is None:
+                return super().computeSpatialAveragedFluxes(F)
+            out = dict.fromkeys(self.theDofManager.idcsOfFieldsInDofVector, 0.0)
+            for field, nDof in self.theDofManager.nAccumulatedNodalFluxesFieldwise.items():
+                host = float(np.linalg.norm(F[self.theDofManager.idcsOfFieldsInDofVector[field]], 1))
+                out[field] = max(1e-10, (flux + host) / nDof)
+            return out
 
         def computeBodyForces(self, bodyForces, U_np, PExt, K, timeStep):
             """Body forces acting on ALL elements run on the device (:516-557); partial element sets stay on the host loop."""

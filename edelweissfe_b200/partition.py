@@ -271,6 +271,16 @@ class SlabAssembly:
         self.poll(group)
         return hP.numpy(), hF.numpy()
 
+    def compute_host_increment(self, dU, flags=0, group=None):
+        """ElementAssembly.compute_host_increment for one rank's slab (after asm.begin_increment): host dU (local numbering) in,
+        (P, sum|F| over this rank's owned dofs) out."""
+        a = self.asm
+        a._increment_upload(dU)
+        self.assemble(flags, group)
+        hP = a._increment_download(self.layout.ownedDofs)  # the ghost plane's entries are the upper neighbour's
+        self.poll(group)
+        return hP.numpy(), float(a._pin_fsum[0])
+
     def poll(self, group=None):
         """Synchronise; every rank takes the same cut-back decision (nonlinearimplicitstatic.py:253-262): in the "peer" exchange the
         status words were combined by the all-reduce of assemble(); the "nccl" exchange reduces a flag here."""

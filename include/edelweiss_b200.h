@@ -66,7 +66,8 @@ enum {
     EWB_FLAG_ACCUMULATE_PF = 1, /* P += , F += (reference semantics on a caller-zeroed vector); default overwrites */
     EWB_FLAG_FORCE_GENERIC = 2, /* use the two-phase VIJ path even when a structured (BoxGen) plan exists */
     EWB_FLAG_NO_STIFFNESS = 4,  /* residual / state only (P, F, stateTemp) */
-    EWB_FLAG_SWEEP_V1 = 8       /* BoxGen plans: the first-generation fused sweep (colour-ordered shared-memory accumulation) instead of the row-pipelined gather sweep */
+    EWB_FLAG_SWEEP_V1 = 8,      /* BoxGen plans: the first-generation fused sweep (colour-ordered shared-memory accumulation) instead of the row-pipelined gather sweep */
+    EWB_FLAG_TWO_PHASE = 16     /* arbitrary-mesh path, 20-node hexahedra: separate element and row-gather kernels instead of the task-stream kernel (same results, bitwise) */
 };
 
 typedef struct ewb_plan ewb_plan; /* opaque: mesh topology + CSR slot tables on one device */
@@ -110,6 +111,12 @@ int ewb_plan_is_box(const ewb_plan* plan);
  * (the host layer passes a Morton order of the coordinates) lets the second read hit L2.  Results do not depend on it.
  * NULL restores the node order.  No counterpart in the reference (csrgenerator.pyx:100-115 is a serial scatter). */
 int ewb_plan_set_gather_order(ewb_plan* plan, const int32_t* order_host);
+/* Optional locality hint for the task-stream kernel of the arbitrary-mesh path (20-node hexahedra): the order (a permutation of
+ * 0..n_el-1, host array) in which the elements are processed.  A node's CSR rows are gathered as soon as its last incident
+ * element is done; processing spatially close elements together (the host layer passes a Morton order of the element
+ * centroids) keeps the element matrices in L2 between the two.  Results do not depend on it (the summation order per node is
+ * always ascending element index = ascending COO index, csrgenerator.pyx:100-115).  NULL restores the element order. */
+int ewb_plan_set_element_order(ewb_plan* plan, const int32_t* order_host);
 
 /* ---- the hot path ---------------------------------------------------------------------------
  * One NIST.computeElements pass + CSRGenerator.updateCSR on the device

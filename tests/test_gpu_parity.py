@@ -493,3 +493,30 @@ def test_current_device_is_preserved():
         s = asm.state_aos("temp")
     assert torch.cuda.current_device() == 0
     assert s.device.index == 1 and bool(torch.isfinite(asm.csr_data).all())
+
+
+def test_compute_host_increment_matches_compute_host():
+    """The lean per-iteration call (U_n device resident, dU in, P + sum|F| out) against the full one (U_np, dU in, P, F out)."""
+    from edelweissfe_b200 import ElementAssembly, box_mesh
+
+    coords, conn = box_mesh(6, 5, 9)
+    rng = np.random.default_rng(5)
+    props = [2.1e4, 0.22, 355, 1000, 200, 1400]
+    full = ElementAssembly("C3D8", conn, coords, "vonmises", props, box=(6, 5, 9))
+    lean = ElementAssembly("C3D8", conn, coords, "vonmises", props, box=(6, 5, 9))
+    U_n = np.zeros(full.nDof)
+    for inc in range(2):
+        lean.begin_increment(U_n)
+        dU = np.zeros(full.nDof)
+        for it in range(2):
+            dU = dU + 3e-3 * rng.standard_normal(full.nDof)
+            P0, F0 = full.compute_host(U_n + dU, dU)
+            P0, F0 = P0.copy(), F0.copy()
+            P1, fsum = lean.compute_host_increment(dU)
+            assert np.array_equal(P0, P1)
+            assert np.array_equal(full.csr_data.cpu().numpy(), lean.csr_data.cpu().numpy())
+            assert np.array_equal(lean.F.cpu().numpy(), F0)
+            assert abs(fsum - np.linalg.norm(F0, 1)) <= 1e-13 * np.linalg.norm(F0, 1)
+        U_n = U_n + dU
+        full.accept_last_state()
+        lean.accept_last_state()

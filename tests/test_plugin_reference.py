@@ -48,6 +48,16 @@ class OracleBackend:
         self.out = o
         return o["P"], o["F"]
 
+    def begin_increment(self, U_n):
+        self.Un = np.array(U_n, dtype=float)
+        self.increments = getattr(self, "increments", 0) + 1
+
+    def compute_host_increment(self, dU, time=(0, 0), dT=0.0, flags=0):
+        dU = np.array(dU, dtype=float)
+        P, F = self.compute_host(self.Un + dU, dU, time=time, dT=dT, flags=flags)
+        self.lean_calls = getattr(self, "lean_calls", 0) + 1
+        return P, float(F.sum())
+
     def body_force_host(self, load):
         elType, material, props, coords, conn = self.args
         self.body_force_calls = getattr(self, "body_force_calls", 0) + 1
@@ -72,6 +82,8 @@ JOBS = ["WallShearHexa8", "TensionBarHexa8", "CantileverBeamHexa8", "WallShearHe
 def test_reference_jobs_through_plugin(testdir):
     U, model, foc, created = jobs.run(jobs.job_text(testdir), testdir, backend=OracleBackend)
     assert created, "the plugin's computeElements was not used"
+    # default b200io=lean: U_n uploaded once per increment, every Newton iteration went through the dU-only call
+    assert created[0].increments >= 1 and created[0].lean_calls >= created[0].increments
     # the reference's own acceptance test: max-abs < 1e-6 (_cli/_run_tests_edelweissfe.py:102-105)
     assert np.abs(U - jobs.uref(testdir)).max() < 1e-6
     # and tighter against the reference's own serial solver on the same machine (what remains is the
@@ -86,6 +98,15 @@ def test_reference_jobs_through_plugin(testdir):
         assert np.isfinite(f[name]).all(), name
         # (the two runs' U differ by up to 1e-8, see above; stresses amplify that by E / h)
         assert np.abs(f[name] - f0[name]).max() <= 1e-5 * np.abs(f0[name]).max() + 1e-12, name
+
+
+def test_full_io_option_matches_lean():
+    """`b200io=full` (U_np, dU in / P, F out, the literal computeElements signature) and the default lean call give the same job result."""
+    src = jobs.job_text("TensionBarHexa8")
+    U_lean, _, _, c1 = jobs.run(src, "TensionBarHexa8", backend=OracleBackend)
+    U_full, _, _, c2 = jobs.run(src, "TensionBarHexa8full", backend=OracleBackend, solver_options="b200io=full")
+    assert getattr(c2[0], "lean_calls", 0) == 0 and c1[0].lean_calls > 0
+    assert np.abs(U_lean - U_full).max() < 1e-12 * max(1.0, np.abs(U_full).max())
 
 
 def test_box_detection_and_state_views():
