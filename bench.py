@@ -354,6 +354,8 @@ def main():
         fixed = np.where(coords_h[:, 1] == coords_h[:, 1].min())[0]  # the y = 0 face (WallShear-style support)
         dofs = torch.as_tensor(np.concatenate([3 * fixed, 3 * fixed + 1, 3 * fixed + 2]).astype(np.int32), device=dev)
 
+        multi = slab is not None and world > 1
+
         def e2e_step(U_in, dU_in):
             # the literal signature of NIST.computeElements (b200io=full): host U_np, dU in, P and F out
             if slab is not None:
@@ -366,10 +368,15 @@ def main():
         def e2e_step_lean(U_in, dU_in):
             # what NISTB200.computeElements + applyDirichletK do per Newton iteration (b200io=lean, b200solver=pcg): U_n is device
             # resident for the increment (like the Gauss-point state), host dU in, P and the flux 1-norm out
-            if slab is not None:
+            if multi:
                 P, fsum = slab.compute_host_increment(dU_in, flags)
-            else:
-                P, fsum = asm.compute_host_increment(dU_in, flags=flags)
+            else:  # + the transfers overlapped with the kernel, x-chunk by x-chunk (copy-in / kernel / copy-out streams)
+                P, fsum = asm.compute_host_increment_pipelined(dU_in, flags=flags)
+            asm.apply_dirichlet_k(dofs)
+            return P, fsum
+
+        def e2e_step_serial(U_in, dU_in):
+            P, fsum = asm.compute_host_increment(dU_in, flags=flags)
             asm.apply_dirichlet_k(dofs)
             return P, fsum
 
@@ -396,17 +403,21 @@ def main():
         dt = timed(e2e_step_lean, None, None)
         # (2) the same with a pageable NumPy dU (what NIST hands the plugin): + the staging copy into the pinned buffer
         dt_pageable = timed(e2e_step_lean, None, dU_np)
+        dt_serial = timed(e2e_step_serial, None, None) if not multi else None
         # (3) the literal computeElements signature: U_np, dU in, P, F out (b200io=full), pinned
         pU[:] = U_np
         dt_full = timed(e2e_step, None, None)
         e2e = {"value": nEl_total / dt / 1e6, "unit": "Melem/s", "h2d_bytes_per_step": int(8 * asm.nDof), "d2h_bytes_per_step": int(8 * asm.nDof + 8),
                "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "note": "ElementAssembly.compute_host_increment + apply_dirichlet_k (the plugin's per-iteration calls, b200io=lean), input in pinned host memory: "
-                       "dU -> device, U_np = U_n + dU on the device (U_n resident for the increment, nonlinearimplicitstatic.py:416-417), assemble, "
-                       "P and sum|F| -> host (the solver only takes the 1-norm of F, :771-792); Gauss-point state and the CSR matrix stay on the device "
-                       "for the device solver (:419-456)",
+               "note": "ElementAssembly.compute_host_increment_pipelined + apply_dirichlet_k (the plugin's per-iteration calls, b200io=lean), input in pinned "
+                       "host memory: dU -> device, U_np = U_n + dU on the device (U_n resident for the increment, nonlinearimplicitstatic.py:416-417), "
+                       "assemble, P and sum|F| -> host (the solver only takes the 1-norm of F, :771-792); Gauss-point state and the CSR matrix stay on the "
+                       "device for the device solver (:419-456); single GPU: upload / kernel / download overlapped x-chunk by x-chunk on three streams",
+               "pipelined_chunks": (len(asm.x_chunks(flags)) - 1 if (not multi and asm.x_chunks(flags)) else 0),
                "pageable_numpy_inputs": {"value": nEl_total / dt_pageable / 1e6, "unit": "Melem/s", "ms_per_step": dt_pageable * 1e3,
                                          "note": "same call with a pageable NumPy dU (what NIST hands the plugin): + one host staging copy"},
+               "serial_transfers": (None if dt_serial is None else {"value": nEl_total / dt_serial / 1e6, "unit": "Melem/s", "ms_per_step": dt_serial * 1e3,
+                                                                    "note": "compute_host_increment: the same call without the chunk pipeline"}),
                "full_signature": {"value": nEl_total / dt_full / 1e6, "unit": "Melem/s", "ms_per_step": dt_full * 1e3,
                                   "h2d_bytes_per_step": int(2 * 8 * asm.nDof), "d2h_bytes_per_step": int(2 * 8 * asm.nDof),
                                   "note": "ElementAssembly.compute_host (b200io=full): U_np, dU -> device, P, F -> host, pinned"}}

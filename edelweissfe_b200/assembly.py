@@ -339,6 +339,127 @@ class ElementAssembly:
         self._pin_fsum.copy_(self._fsum, non_blocking=True)
         return hP
 
+    def _registered_input(self, arr):
+        """A pageable NumPy array the caller keeps re-using (the solver's dU lives for a whole step, nonlinearimplicitstatic.py:163)
+        as a pinned torch tensor: the array's memory is registered with the driver once (cudaHostRegister) and unregistered when
+        the array is garbage collected, so that its upload needs no staging copy.  None when that is not possible."""
+        import weakref
+
+        if os.environ.get("EWB_HOST_REGISTER", "1") != "1":
+            return None
+        arr = np.asarray(arr)
+        if arr.dtype != np.float64 or not arr.flags["C_CONTIGUOUS"] or arr.nbytes < int(os.environ.get("EWB_HOST_REGISTER_MIN", 1 << 20)):
+            return None
+        reg = self.__dict__.setdefault("_registered", {})
+        key = (arr.ctypes.data, arr.nbytes)
+        if key not in reg:
+            owner = arr
+            while isinstance(getattr(owner, "base", None), np.ndarray):  # register / track the array that owns the memory
+                owner = owner.base
+            if owner.ctypes.data != arr.ctypes.data or owner.nbytes != arr.nbytes:
+                return None
+            rt = torch.cuda.cudart()
+            if int(rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)) != 0:
+                return None
+            ptr = arr.ctypes.data
+
+            def _release(ptr=ptr, key=key, reg=reg):
+                reg.pop(key, None)
+                try:
+                    torch.cuda.cudart().cudaHostUnregister(ptr)
+                except Exception:  # noqa: BLE001 - interpreter shutdown
+                    pass
+
+            try:
+                weakref.finalize(owner, _release)
+            except TypeError:
+                rt.cudaHostUnregister(ptr)
+                return None
+            reg[key] = True
+        t = torch.from_numpy(arr.reshape(-1))
+        return t if t.is_pinned() else None
+
+    def x_chunks(self, flags=0):
+        """Node-plane boundaries of the fused kernel's independent x-chunks (ewb_plan_x_chunks), or None when this plan does not
+        run the chunked kernel.  Cached per flags."""
+        cache = self.__dict__.setdefault("_x_chunks", {})
+        if flags not in cache:
+            bounds = (C.c_int32 * 130)()
+            n = check(self.lib.ewb_plan_x_chunks(self.plan, self.matCode, self._props_c, len(self.props), int(flags), bounds, 130))
+            cache[flags] = None if n <= 0 else [int(bounds[i]) for i in range(n + 1)]
+        return cache[flags]
+
+    def _pipeline_streams(self):
+        st = getattr(self, "_pipe_streams", None)
+        if st is None:
+            with torch.cuda.device(self.device):
+                st = self._pipe_streams = dict(h2d=torch.cuda.Stream(), d2h=torch.cuda.Stream(), k=[torch.cuda.Stream(), torch.cuda.Stream()])
+        return st
+
+    def _increment_pipelined(self, dU, bounds, flags, launch=None, n_owned=None):
+        """The chunk pipeline behind compute_host_increment: for every x-chunk c  [upload dU of its node planes, U = U_n + dU] ->
+        [kernel of chunk c] -> [download P of its node planes], on a copy-in stream, two alternating kernel streams and a copy-out
+        stream (PCIe is full duplex; kernels of different chunks are independent and fill the SMs together)."""
+        hdU, hP = self._pinned("dU", self.nDof), self._pinned("P", self.nDof)
+        hdU_np = hdU.numpy()
+        dU = None if dU is None else np.asarray(dU)
+        if dU is not None:
+            reg = self._registered_input(dU)  # upload straight from the caller's array when it can be pinned in place
+            if reg is not None:
+                hdU, dU = reg, None
+        st = self._pipeline_streams()
+        cur = torch.cuda.current_stream(self.device)
+        start = torch.cuda.Event()
+        start.record(cur)
+        for s in (st["h2d"], st["d2h"], *st["k"]):
+            s.wait_event(start)
+        nPlanes = bounds[-1]
+        pd = self.nDof // nPlanes  # dofs per node plane
+        buf = self._buffers()
+        done = []
+        for c in range(len(bounds) - 1):
+            lo = 0 if c == 0 else (bounds[c] + 1) * pd  # chunk c reads planes [bounds[c] - 1, bounds[c + 1]]: the new ones
+            hi = min(bounds[c + 1] + 1, nPlanes) * pd
+            if dU is not None and hi > lo:
+                hdU_np[lo:hi] = dU[lo:hi]  # pageable input: staged chunk by chunk, behind the previous chunk's upload and kernel
+            with torch.cuda.stream(st["h2d"]):
+                if hi > lo:
+                    self.dU[lo:hi].copy_(hdU[lo:hi], non_blocking=True)
+                    torch.add(self.Un[lo:hi], self.dU[lo:hi], out=self.U[lo:hi])
+                up = torch.cuda.Event()
+                up.record(st["h2d"])
+            ks = st["k"][c & 1]
+            ks.wait_event(up)
+            if launch is None:
+                check(self.lib.ewb_assemble_chunks(self.plan, self.matCode, self._props_c, len(self.props), C.byref(buf), int(flags), c, c + 1,
+                                                   C.c_void_p(ks.cuda_stream)))
+            else:
+                launch(c, ks)
+            kd = torch.cuda.Event()
+            kd.record(ks)
+            done.append(kd)
+            if launch is None:  # (a slab's first plane still receives the lower neighbour's rows: its P is downloaded at the end)
+                st["d2h"].wait_event(kd)
+                with torch.cuda.stream(st["d2h"]):
+                    a, b = bounds[c] * pd, bounds[c + 1] * pd
+                    hP[a:b].copy_(self.P[a:b], non_blocking=True)
+        for kd in done:
+            cur.wait_event(kd)
+        return hP
+
+    def compute_host_increment_pipelined(self, dU, flags=0):
+        """compute_host_increment with the transfers overlapped chunk by chunk (BoxGen plans on the fused kernel; falls back to the
+        plain call otherwise).  Same results, bitwise."""
+        bounds = self.x_chunks(flags)
+        if bounds is None or len(bounds) < 3 or getattr(self, "Un", None) is None:
+            return self.compute_host_increment(dU, flags=flags)
+        hP = self._increment_pipelined(dU, bounds, flags)
+        torch.sum(self.F, dim=0, keepdim=True, out=self._fsum)
+        self._pin_fsum.copy_(self._fsum, non_blocking=True)
+        torch.cuda.current_stream(self.device).wait_stream(self._pipe_streams["d2h"])
+        self.poll()
+        return hP.numpy(), float(self._pin_fsum[0])
+
     def compute_host_increment(self, dU, time=(0.0, 0.0), dT=0.0, flags=0):
         """One Newton iteration of the current increment with HOST dU (after begin_increment): returns (P, sum|F|).  P is a view of
         a pinned buffer (valid until the next call); F itself stays on the device (self.F) — the solver only ever takes its 1-norm

@@ -743,6 +743,58 @@ int ewb_assemble(ewb_plan* p, int material, const double* props, int n_props, co
     return EWB_OK;
 }
 
+// ---- pipelined host I/O: the x-chunks of the row-pipelined kernel as separate launches -------------------------------------
+namespace {
+// variant of the automatic choice in ewb_assemble; 0 when the plan / material does not run the row-pipelined kernel
+int rowPipeVariantOf(const ewb_plan* p, int mc, int flags) {
+    if (!p->isBox || (flags & (EWB_FLAG_FORCE_GENERIC | EWB_FLAG_SWEEP_V1)) || !p->sweep.indexable()) return 0;
+    const int variant = p->fusedVariant != 0 ? p->fusedVariant : (mc == ewb::MC_LE ? 4040804 : (mc == ewb::MC_VM ? 9040804 : 8040804));
+    return variant == 1 ? 0 : variant;
+}
+}  // namespace
+
+int ewb_plan_x_chunks(ewb_plan* p, int material, const double* props, int n_props, int flags, int32_t* bounds_out, int max_bounds) {
+    if (!p || !props || !bounds_out || max_bounds < 2) return fail(EWB_ERR_ARG, "ewb_plan_x_chunks: bad arguments");
+    WITH_DEVICE(p->device);
+    ewb::MatParams mp; int mc, nms;
+    if (int rc = materialClass(p->elType, material, props, n_props, &mp, &mc, &nms)) return rc;
+    const int variant = rowPipeVariantOf(p, mc, flags);
+    if (!variant) return 0;
+    int tiling[2] = {0, 0};
+    ewb_buffers dummy;
+    std::memset(&dummy, 0, sizeof(dummy));
+    p->sweep.tilingOut = tiling;
+    const int rc = ewb::launchRowPipeAny(p->sweep, variant, p->elType, mc, mp, &dummy, p->failFlag, flags, nullptr);
+    p->sweep.tilingOut = nullptr;
+    if (rc == EWB_ERR_UNSUPPORTED) return 0;
+    if (rc != EWB_OK) return fail(rc, "ewb_plan_x_chunks: tiling query failed");
+    const int n = tiling[1];
+    if (n + 1 > max_bounds) return fail(EWB_ERR_ARG, "ewb_plan_x_chunks: bounds_out too small");
+    for (int c = 0; c <= n; ++c) bounds_out[c] = (int32_t)std::min<int64_t>((int64_t)c * tiling[0], p->nX + 1);
+    return n;
+}
+
+int ewb_assemble_chunks(ewb_plan* p, int material, const double* props, int n_props, const ewb_buffers* b, int flags, int chunk_begin, int chunk_end,
+                        void* stream) {
+    if (!p || !b || !props) return fail(EWB_ERR_ARG, "ewb_assemble_chunks: bad arguments");
+    if (!b->coords || !b->U || !b->dU || !b->state_ref || !b->state_temp || !b->P || !b->F) return fail(EWB_ERR_ARG, "ewb_assemble_chunks: null buffer");
+    if (!(flags & EWB_FLAG_NO_STIFFNESS) && !b->csr_data) return fail(EWB_ERR_ARG, "ewb_assemble_chunks: csr_data is null");
+    WITH_DEVICE(p->device);
+    ewb::MatParams mp; int mc, nms;
+    if (int rc = materialClass(p->elType, material, props, n_props, &mp, &mc, &nms)) return rc;
+    const int variant = rowPipeVariantOf(p, mc, flags);
+    if (!variant || b->vij != nullptr) return fail(EWB_ERR_UNSUPPORTED, "ewb_assemble_chunks: needs a BoxGen plan on the row-pipelined kernel (ewb_plan_x_chunks > 0)");
+    p->sweep.chunkBegin = chunk_begin;
+    p->sweep.chunkEnd = chunk_end;
+    const int rc = ewb::launchRowPipeAny(p->sweep, variant, p->elType, mc, mp, b, p->failFlag, flags, (cudaStream_t)stream);
+    p->sweep.chunkBegin = 0;
+    p->sweep.chunkEnd = -1;
+    if (rc == EWB_ERR_ARG) return fail(rc, "ewb_assemble_chunks: chunk range out of bounds");
+    if (rc != EWB_OK) return fail(rc, std::string("ewb_assemble_chunks: launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    countLaunch();
+    return EWB_OK;
+}
+
 int ewb_body_force(ewb_plan* p, const double* coords_dev, const double load_host[3], double* pext_dev, void* stream) {
     if (!p || !coords_dev || !load_host || !pext_dev) return fail(EWB_ERR_ARG, "ewb_body_force: bad arguments");
     WITH_DEVICE(p->device);

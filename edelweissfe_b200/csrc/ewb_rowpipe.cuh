@@ -129,7 +129,7 @@ __global__ void __launch_bounds__((NPW + NTW + NGW) * 32, 1) rowPipeKernel(const
     int item = blockIdx.x;
     const int tz = item % A.tilesZ; item /= A.tilesZ;
     const int ty = item % A.tilesY; item /= A.tilesY;
-    const int chunk = item;
+    const int chunk = item + A.chunkBase;
     const int y0 = ty * A.tileRows, z0 = tz * TZ;
     const int ny = min(A.tileRows, NY - y0), nz = min(TZ, NZ - z0);  // owned node rows / columns
     const int xa = chunk * A.chunkLen, xb = min(xa + A.chunkLen, NX);
@@ -654,7 +654,15 @@ int launchRowPipe(SweepPlan& sp, const MatParams& mp, const ewb_buffers* b, int*
     sp.fillCommon(a, mp, b, failFlag, flags);
     const RowPipeTiling t = rowPipeTiling<TZ>(sp.nX, sp.nY, sp.nZ, sp.nSM, rowsMax, sp.chunkOverride);
     a.tilesY = t.tilesY; a.tilesZ = t.tilesZ; a.tileRows = t.tileRows; a.chunkLen = t.chunkLen; a.nChunks = t.nChunks;
-    const int64_t grid = (int64_t)a.tilesY * a.tilesZ * a.nChunks;
+    if (sp.tilingOut != nullptr) {  // query only (ewb_plan_x_chunks)
+        sp.tilingOut[0] = t.chunkLen;
+        sp.tilingOut[1] = t.nChunks;
+        return EWB_OK;
+    }
+    const int c0 = sp.chunkEnd < 0 ? 0 : sp.chunkBegin, c1 = sp.chunkEnd < 0 ? t.nChunks : sp.chunkEnd;
+    if (c0 < 0 || c1 > t.nChunks || c0 >= c1) return EWB_ERR_ARG;
+    a.chunkBase = c0;
+    const int64_t grid = (int64_t)a.tilesY * a.tilesZ * (c1 - c0);
 #ifdef EWB_TIMING
     {
         const size_t nT = (size_t)grid * (NPW + NTW + NGW) * 8;

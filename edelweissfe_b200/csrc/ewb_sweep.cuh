@@ -30,6 +30,7 @@ struct SweepArgs {
     int nX, nY, nZ;  // elements
     int chunkLen, nChunks, tilesY, tilesZ;
     int tileRows;  // row-pipelined kernel: node rows (y) per tile
+    int chunkBase;  // row-pipelined kernel: first x-chunk of this launch (ewb_assemble_chunks: pipelined host I/O)
     const double* coords;
     const double* U;
     const double* dU;
@@ -1448,6 +1449,10 @@ struct SweepPlan {
     int64_t nX = 0, nY = 0, nZ = 0;
     int nSM = 148;
     int chunkOverride = 0;  // EWB_CHUNKS (tuning knob, read once at plan creation)
+    // row-pipelined kernel, set around a launch by ewb_plan_x_chunks / ewb_assemble_chunks: x-chunk range of the launch
+    // (chunkEnd < 0: all chunks) and, when tilingOut is set, "report the tiling instead of launching"
+    int chunkBegin = 0, chunkEnd = -1;
+    int* tilingOut = nullptr;  // [2]: chunkLen, nChunks
     int spinNs = 0;         // EWB_SPIN_NS
     long long* timingBuf = nullptr;
     size_t timingCount = 0;
@@ -1475,6 +1480,7 @@ struct SweepPlan {
         a.spinNs = spinNs;
         a.timing = nullptr;
         a.tileRows = 0;
+        a.chunkBase = 0;
         a.coords = b->coords; a.U = b->U; a.dU = b->dU; a.stateRef = b->state_ref; a.stateTemp = b->state_temp;
         a.data = b->csr_data; a.P = b->P; a.F = b->F; a.mp = mp; a.failFlag = failFlag;
         a.wantK = (flags & EWB_FLAG_NO_STIFFNESS) ? 0 : 1;

@@ -210,7 +210,11 @@ def make_solver_class(backend_factory=default_backend):
                     if not self._b200_Un_sent:
                         asm.begin_increment(np.asarray(self._b200_Un))
                         self._b200_Un_sent = True
-                    Pel, self._b200_flux = asm.compute_host_increment(np.asarray(dU), **tm)  # U_np = U_n + dU on the device (:416-417)
+                    # U_np = U_n + dU on the device (:416-417); BoxGen plans overlap the transfers with the kernel chunk by chunk
+                    if hasattr(asm, "compute_host_increment_pipelined"):
+                        Pel, self._b200_flux = asm.compute_host_increment_pipelined(np.asarray(dU))
+                    else:
+                        Pel, self._b200_flux = asm.compute_host_increment(np.asarray(dU), **tm)
                 else:
                     Pel, Fel = asm.compute_host(np.asarray(U_np), np.asarray(dU), **tm)
                     self._b200_flux = None

@@ -123,6 +123,16 @@ int ewb_plan_set_element_order(ewb_plan* plan, const int32_t* order_host);
  * (solvers/nonlinearimplicitstatic.py:794-849, 753-769).  Asynchronous on `stream`. */
 int ewb_assemble(ewb_plan* plan, int material, const double* props_host, int n_props, const ewb_buffers* buf,
                  const double time[2], double dT, int flags, void* stream);
+/* Pipelined host I/O for BoxGen plans.  The fused kernel cuts the box into x-chunks of node planes whose CTAs are independent
+ * (a chunk re-computes the element plane below its first node plane): chunk c writes the CSR rows, P and F of the node planes
+ * [bounds[c], bounds[c+1]) and reads U / dU of the node planes [bounds[c] - 1, bounds[c+1]].  Launched chunk by chunk on its own
+ * streams, the upload of the next chunk's dU and the download of the previous chunk's P overlap the kernel (BoxGen numbers nodes
+ * x-major, generators/boxgen.py:133-136, so a chunk's dofs are one contiguous range).  Same results as ewb_assemble, bitwise.
+ * ewb_plan_x_chunks: writes the n + 1 node-plane boundaries, returns n, or 0 when this plan / material / flags combination does
+ * not run the chunked kernel (use ewb_assemble).  No counterpart in the reference (its element loop is serial). */
+int ewb_plan_x_chunks(ewb_plan* plan, int material, const double* props_host, int n_props, int flags, int32_t* bounds_out, int max_bounds);
+int ewb_assemble_chunks(ewb_plan* plan, int material, const double* props_host, int n_props, const ewb_buffers* buf, int flags,
+                        int chunk_begin, int chunk_end, void* stream);
 /* Synchronises `stream`, returns EWB_OK or EWB_CUTBACK (then *pNewDT = 0.5). */
 int ewb_poll_status(ewb_plan* plan, void* stream, double* pNewDT);
 

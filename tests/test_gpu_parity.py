@@ -520,3 +520,42 @@ def test_compute_host_increment_matches_compute_host():
         U_n = U_n + dU
         full.accept_last_state()
         lean.accept_last_state()
+
+
+@pytest.mark.parametrize("material,props", [("linearelastic", [2.1e4, 0.22]), ("vonmises", [2.1e4, 0.22, 355, 1000, 200, 1400])])
+def test_chunk_pipelined_increment_is_bitwise(material, props, monkeypatch):
+    """compute_host_increment_pipelined (x-chunks as separate launches on their own streams, transfers overlapped) against the plain
+    lean call: same kernel, same chunks -> identical bits; and ewb_assemble_chunks over all chunks == ewb_assemble."""
+    from edelweissfe_b200 import ElementAssembly, box_mesh
+
+    monkeypatch.setenv("EWB_CHUNKS", "3")  # force three x-chunks on a small box (read at plan creation)
+    monkeypatch.setenv("EWB_HOST_REGISTER_MIN", "0")  # exercise the in-place pinning of the caller's dU on this small vector too
+    n = (13, 9, 10)
+    coords, conn = box_mesh(*n)
+    rng = np.random.default_rng(8)
+    a0 = ElementAssembly("C3D8", conn, coords, material, props, box=n)
+    a1 = ElementAssembly("C3D8", conn, coords, material, props, box=n)
+    bounds = a1.x_chunks()
+    assert bounds is not None and len(bounds) == 4 and bounds[0] == 0 and bounds[-1] == n[0] + 1
+    U_n = 1e-3 * rng.standard_normal(a0.nDof)
+    a0.begin_increment(U_n)
+    a1.begin_increment(U_n)
+    for it in range(3):
+        dU = 3e-3 * rng.standard_normal(a0.nDof)
+        a1.csr_data.fill_(float("nan"))
+        a1.P.fill_(float("nan"))
+        P0, f0 = a0.compute_host_increment(dU)
+        P0 = P0.copy()
+        P1, f1 = a1.compute_host_increment_pipelined(dU)
+        assert np.array_equal(P0, P1) and f0 == f1
+        assert (dU.ctypes.data, dU.nbytes) in a1._registered  # uploaded from the caller's own (now pinned) array
+        P1b, _ = a1.compute_host_increment_pipelined(dU)  # same array again: registered once
+        assert np.array_equal(P0, P1b)
+        for name in ("csr_data", "F", "state_temp", "U", "dU"):
+            assert np.array_equal(getattr(a0, name).cpu().numpy(), getattr(a1, name).cpu().numpy()), name
+    # generic path (no chunked kernel): the pipelined call falls back
+    a2 = ElementAssembly("C3D8", conn, coords, material, props)  # no box
+    assert a2.x_chunks() is None
+    a2.begin_increment(U_n)
+    P2, f2 = a2.compute_host_increment_pipelined(dU)
+    assert np.abs(P2 - P0).max() <= 1e-12 * np.abs(P0).max()
