@@ -369,14 +369,17 @@ def main():
             # what NISTB200.computeElements + applyDirichletK do per Newton iteration (b200io=lean, b200solver=pcg): U_n is device
             # resident for the increment (like the Gauss-point state), host dU in, P and the flux 1-norm out
             if multi:
-                P, fsum = slab.compute_host_increment(dU_in, flags)
+                P, fsum = slab.compute_host_increment_pipelined(dU_in, flags)
             else:  # + the transfers overlapped with the kernel, x-chunk by x-chunk (copy-in / kernel / copy-out streams)
                 P, fsum = asm.compute_host_increment_pipelined(dU_in, flags=flags)
             asm.apply_dirichlet_k(dofs)
             return P, fsum
 
         def e2e_step_serial(U_in, dU_in):
-            P, fsum = asm.compute_host_increment(dU_in, flags=flags)
+            if multi:
+                P, fsum = slab.compute_host_increment(dU_in, flags)
+            else:
+                P, fsum = asm.compute_host_increment(dU_in, flags=flags)
             asm.apply_dirichlet_k(dofs)
             return P, fsum
 
@@ -403,7 +406,7 @@ def main():
         dt = timed(e2e_step_lean, None, None)
         # (2) the same with a pageable NumPy dU (what NIST hands the plugin): + the staging copy into the pinned buffer
         dt_pageable = timed(e2e_step_lean, None, dU_np)
-        dt_serial = timed(e2e_step_serial, None, None) if not multi else None
+        dt_serial = timed(e2e_step_serial, None, None)
         # (3) the literal computeElements signature: U_np, dU in, P, F out (b200io=full), pinned
         pU[:] = U_np
         dt_full = timed(e2e_step, None, None)
@@ -412,8 +415,8 @@ def main():
                "note": "ElementAssembly.compute_host_increment_pipelined + apply_dirichlet_k (the plugin's per-iteration calls, b200io=lean), input in pinned "
                        "host memory: dU -> device, U_np = U_n + dU on the device (U_n resident for the increment, nonlinearimplicitstatic.py:416-417), "
                        "assemble, P and sum|F| -> host (the solver only takes the 1-norm of F, :771-792); Gauss-point state and the CSR matrix stay on the "
-                       "device for the device solver (:419-456); single GPU: upload / kernel / download overlapped x-chunk by x-chunk on three streams",
-               "pipelined_chunks": (len(asm.x_chunks(flags)) - 1 if (not multi and asm.x_chunks(flags)) else 0),
+                       "device for the device solver (:419-456); upload / kernel / download overlapped x-chunk by x-chunk on three streams",
+               "pipelined_chunks": (len(asm.x_chunks(flags)) - 1 if asm.x_chunks(flags) else 0),
                "pageable_numpy_inputs": {"value": nEl_total / dt_pageable / 1e6, "unit": "Melem/s", "ms_per_step": dt_pageable * 1e3,
                                          "note": "same call with a pageable NumPy dU (what NIST hands the plugin): + one host staging copy"},
                "serial_transfers": (None if dt_serial is None else {"value": nEl_total / dt_serial / 1e6, "unit": "Melem/s", "ms_per_step": dt_serial * 1e3,

@@ -225,6 +225,24 @@ class SlabAssembly:
 
     def assemble(self, flags=0, group=None):
         """Local fused assembly, then the neighbour exchange and the interface add (all on the current stream)."""
+        par = self._before_kernel()
+        self.asm.assemble(flags)
+        self._after_kernel(par, group)
+
+    def _before_kernel(self):
+        """"peer" exchange: point the fused kernel at this assembly's half of the upper neighbour's (double buffered) receive buffer."""
+        from ._lib import check
+
+        a, lay = self.asm, self.layout
+        par = self.step & 1  # receive buffers are double buffered: a fast sender may already be one assembly ahead
+        if self.exchange == "peer" and lay.has_upper:
+            base = self._peer + 8 * par * self._peer_seg
+            check(a.lib.ewb_plan_set_peer(a.plan, C.c_void_p(base), C.c_void_p(base + 8 * self._peer_head),
+                                          C.c_void_p(base + 8 * (self._peer_head + lay.planeDofs))))
+        return par
+
+    def _after_kernel(self, par, group=None):
+        """Neighbour exchange (or, for "peer", the status all-reduce that orders it) and the interface add, on the current stream."""
         import torch.distributed as dist
 
         from ._lib import check
@@ -232,22 +250,14 @@ class SlabAssembly:
         a, lay = self.asm, self.layout
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
         if self.exchange == "peer":
-            par = self.step & 1  # receive buffers are double buffered: a fast sender may already be one assembly ahead
-            if lay.has_upper:
-                base = self._peer + 8 * par * self._peer_seg
-                check(a.lib.ewb_plan_set_peer(a.plan, C.c_void_p(base), C.c_void_p(base + 8 * self._peer_head),
-                                              C.c_void_p(base + 8 * (self._peer_head + lay.planeDofs))))
-            a.assemble(flags)
             # orders the neighbour's peer stores before the interface add; every rank sees the same cut-back request
             # NCCL has no bitwise reductions: MAX gives every rank the SAME word, in which an error bit (4: internal, 8: inverted
             # element) outranks the cut-back bit (1) — errors abort the step on all ranks, a cut-back alone reaches all ranks as 1
             dist.all_reduce(self.status, op=dist.ReduceOp.MAX, group=group)
             if lay.has_lower:
                 self.recv, self.recvP, self.recvF = self._views[par]
-        else:
-            a.assemble(flags)
-            if lay.world > 1:
-                exchange_tails(lay, a.csr_data, a.P, a.F, self.recv, self.recvP, self.recvF, self.indptr_host, dist, group)
+        elif lay.world > 1:
+            exchange_tails(lay, a.csr_data, a.P, a.F, self.recv, self.recvP, self.recvF, self.indptr_host, dist, group)
         if lay.has_lower:
             check(a.lib.ewb_interface_add(p(self.indptr), lay.planeDofs, p(a.csr_data), p(self.recv), p(a.P), p(a.F), p(self.recvP), p(self.recvF),
                                           a._stream()))
@@ -278,6 +288,28 @@ class SlabAssembly:
         a._increment_upload(dU)
         self.assemble(flags, group)
         hP = a._increment_download(self.layout.ownedDofs)  # the ghost plane's entries are the upper neighbour's
+        self.poll(group)
+        return hP.numpy(), float(a._pin_fsum[0])
+
+    def compute_host_increment_pipelined(self, dU, flags=0, group=None):
+        """compute_host_increment with the host transfers overlapped with the kernel x-chunk by x-chunk
+        (ElementAssembly._increment_pipelined); the exchange and the interface add follow the last chunk, and the first node
+        plane of P — the only part the interface add changes — is downloaded again after it.  Same results, bitwise."""
+        import torch
+
+        a, lay = self.asm, self.layout
+        bounds = a.x_chunks(flags)
+        if bounds is None or len(bounds) < 3 or getattr(a, "Un", None) is None:
+            return self.compute_host_increment(dU, flags, group)
+        par = self._before_kernel()
+        hP = a._increment_pipelined(dU, bounds, flags)
+        self._after_kernel(par, group)
+        cur = torch.cuda.current_stream(a.device)
+        cur.wait_stream(a._pipe_streams["d2h"])
+        if lay.has_lower:
+            hP[: lay.planeDofs].copy_(a.P[: lay.planeDofs], non_blocking=True)
+        torch.sum(a.F[: lay.ownedDofs], dim=0, keepdim=True, out=a._fsum)
+        a._pin_fsum.copy_(a._fsum, non_blocking=True)
         self.poll(group)
         return hP.numpy(), float(a._pin_fsum[0])
 
@@ -345,9 +377,27 @@ def slab_parity_check(world, rank, device, n=None, elType="C3D8", material="vonm
     for _ in range(3):  # repeated assemblies: the double-buffered receive side must stay consistent
         slab.assemble(group=group)
     slab.poll(group)
+    # the host-facing calls of the same slab: full (U, dU in / P, F out), lean (dU in / P, sum|F| out) and lean with the transfers
+    # pipelined over the kernel's x-chunks must agree bit for bit with the device-resident assembly above
+    host_ok = 1
+    Pd, Fd = asm.P.cpu().numpy().copy(), asm.F.cpu().numpy().copy()
+    _, own_nnz = slab.owned_slices()
+    Kd = asm.csr_data[own_nnz].clone()
+    Pf, Ff = slab.compute_host(ldU, ldU, group=group)
+    host_ok &= int(np.array_equal(Pf[: lay.ownedDofs], Pd[: lay.ownedDofs]) and np.array_equal(Ff[: lay.ownedDofs], Fd[: lay.ownedDofs]))
+    asm.begin_increment(np.zeros_like(ldU))
+    Pl, fl = slab.compute_host_increment(ldU, group=group)
+    host_ok &= int(np.array_equal(Pl[: lay.ownedDofs], Pd[: lay.ownedDofs]))
+    Pl = Pl.copy()
+    asm.csr_data.fill_(float("nan"))
+    Pp, fp = slab.compute_host_increment_pipelined(ldU, group=group)
+    host_ok &= int(np.array_equal(Pp[: lay.ownedDofs], Pl[: lay.ownedDofs]) and fp == fl and bool(torch.equal(asm.csr_data[own_nnz], Kd)))
+    host_ok &= int(abs(fl - Fd[: lay.ownedDofs].sum()) <= 1e-12 * abs(fl))
+    chunks = asm.x_chunks()
     rows, nnzs = slab.owned_slices()
     mine = (rank, 3 * n0, slab.indptr_host[: lay.ownedDofs + 1].copy(), slab.indices.cpu().numpy()[nnzs], asm.csr_data.cpu().numpy()[nnzs],
-            asm.P.cpu().numpy()[rows], asm.F.cpu().numpy()[rows], slab.recv.cpu().numpy(), lay.planeDofs, lay.has_lower, slab.exchange)
+            asm.P.cpu().numpy()[rows], asm.F.cpu().numpy()[rows], slab.recv.cpu().numpy(), lay.planeDofs, lay.has_lower,
+            (slab.exchange, host_ok, 0 if chunks is None else len(chunks) - 1))
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(mine, gathered, dst=0, group=group)
     slab.close()
@@ -363,7 +413,9 @@ def slab_parity_check(world, rank, device, n=None, elType="C3D8", material="vonm
     nG = Kg.shape[0]
     scale = abs(Kg).max()
     worst = 0.0
-    for _r, off, indptr, indices, data, P, F, recv, planeDofs, has_lower, _ex in gathered:
+    for _r, off, indptr, indices, data, P, F, recv, planeDofs, has_lower, (_ex, host_ok, _nch) in gathered:
+        if not host_ok:
+            worst = max(worst, 1.0)  # a host-facing call disagreed with the device-resident assembly
         nrows = indptr.size - 1
         Kl = sp.csr_matrix((data, indices.astype(np.int64) + off, indptr), shape=(nrows, nG))
         Kref = Kg[off : off + nrows]

@@ -17,7 +17,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port_no, q, exchange, material):
+def _worker(rank, world, port_no, q, exchange, material, n=(9, 8, 7), chunks=None):
     import torch
     import torch.distributed as dist
 
@@ -26,20 +26,24 @@ def _worker(rank, world, port_no, q, exchange, material):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)
     os.environ["EWB_EXCHANGE"] = exchange
+    if chunks:
+        os.environ["EWB_CHUNKS"] = str(chunks)  # x-chunks of the fused kernel (read at plan creation): exercises the chunk pipeline
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         props = {"vonmises": (2.1e4, 0.22, 355.0, 1000.0, 200.0, 1400.0), "linearelastic": (2.1e4, 0.22)}[material]
-        err = slab_parity_check(world, rank, torch.device("cuda", rank), n=(9, 8, 7), material=material, props=props)
+        err = slab_parity_check(world, rank, torch.device("cuda", rank), n=n, material=material, props=props)
         q.put((rank, err))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])  # 4: ranks with BOTH neighbours (receive from below, store to the rank above)
+@pytest.mark.parametrize("world,n,chunks", [(2, (9, 8, 7), None), (4, (9, 8, 7), None), (2, (19, 8, 7), 2)])
+# 4: ranks with BOTH neighbours (receive from below, store to the rank above); chunks=2: the host calls' transfers are pipelined
+# over two x-chunks per rank (slab_parity_check compares them with the device-resident assembly)
 @pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("material", ["vonmises", "linearelastic"])  # first-generation sweep / row-pipelined kernel
-def test_slabs_match_single_gpu(exchange, world, material):
+def test_slabs_match_single_gpu(exchange, world, n, chunks, material):
     import torch
 
     if torch.cuda.device_count() < world:
@@ -49,7 +53,7 @@ def test_slabs_match_single_gpu(exchange, world, material):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port_no = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port_no, q, exchange, material)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port_no, q, exchange, material, n, chunks)) for r in range(world)]
     for p in procs:
         p.start()
     try:
