@@ -641,6 +641,8 @@ inline RowPipeTiling rowPipeTiling(int64_t nX, int64_t nY, int64_t nZ, int nSM, 
         }
         if (rows == 1) break;
     }
+    // an override that no tile shape accepts (chunks shorter than four planes) is ignored rather than leaving the placeholder tiling
+    if (bestCost == 1e300 && chunkOverride > 0) return rowPipeTiling<TZ>(nX, nY, nZ, nSM, rowsMax, 0);
     return best;
 }
 
