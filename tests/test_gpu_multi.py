@@ -38,7 +38,7 @@ def _worker(rank, world, port_no, q, exchange, material, n=(9, 8, 7), chunks=Non
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,chunks", [(2, (9, 8, 7), None), (4, (9, 8, 7), None), (2, (19, 8, 7), 2)])
+@pytest.mark.parametrize("world,n,chunks", [(2, (9, 8, 7), None), (4, (9, 8, 7), None), (2, (19, 8, 7), 2), (4, (35, 8, 7), 2)])
 # 4: ranks with BOTH neighbours (receive from below, store to the rank above); chunks=2: the host calls' transfers are pipelined
 # over two x-chunks per rank (slab_parity_check compares them with the device-resident assembly)
 @pytest.mark.parametrize("exchange", ["peer", "nccl"])
