@@ -38,10 +38,3 @@ def box_mesh(nX, nY, nZ, lX=1.0, lY=1.0, lZ=1.0, x0=0.0, y0=0.0, z0=0.0, elType=
         coords = coords[keep]
         grid = renum[grid]
     return np.ascontiguousarray(coords), np.ascontiguousarray(grid.astype(np.int32))
-
-
-def node_sets(nX, nY, nZ):
-    """Hexa8 node index sets named like boxgen.py:334-418 (left/right = x faces, bottom/top = y, back/front = z)."""
-    NX, NY, NZ = nX + 1, nY + 1, nZ + 1
-    n = np.arange(NX * NY * NZ).reshape(NX, NY, NZ)
-    return dict(left=n[0].ravel(), right=n[-1].ravel(), bottom=n[:, 0].ravel(), top=n[:, -1].ravel(), back=n[:, :, 0].ravel(), front=n[:, :, -1].ravel())
