@@ -325,6 +325,8 @@ class ElementAssembly:
         self.Un.copy_(hU, non_blocking=True)
 
     def _increment_upload(self, dU):
+        if getattr(self, "Un", None) is None:
+            raise EwbError("compute_host_increment needs begin_increment(U_n) first (U_n of the increment is device resident)")
         hdU = self._pinned("dU", self.nDof)
         if dU is not None:
             hdU.numpy()[:] = dU
