@@ -64,6 +64,7 @@ SYMBOLS = {
     "ewb_plan_is_box": (C.c_int, [_P]),
     "ewb_plan_set_gather_order": (C.c_int, [_P, _P]),
     "ewb_plan_set_element_order": (C.c_int, [_P, _P]),
+    "ewb_debug_stream_schedule": (C.c_int64, [C.c_int, C.c_int64, C.c_int64, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P, _P, C.c_int64]),
     "ewb_assemble": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(EwbBuffers), C.POINTER(C.c_double), C.c_double, C.c_int, _P]),
     "ewb_plan_x_chunks": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, _P, C.c_int]),
     "ewb_assemble_chunks": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(EwbBuffers), C.c_int, C.c_int, C.c_int, _P]),

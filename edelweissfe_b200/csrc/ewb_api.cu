@@ -214,37 +214,33 @@ void streamRelease(ewb_plan* p) {
     p->streamBuilt = false;
 }
 
-int streamBuild(ewb_plan* p) {
-    streamRelease(p);
-    const int64_t nEl = p->nEl, nNode = p->nNode;
-    const int nn = p->nn;
-    const int64_t CE = p->streamChunk;
-    const int EPT = p->streamElPerTask, NPT = p->streamNodesPerTask, D = p->streamDelay;
+// Pure host part (no CUDA; also behind the test hook ewb_debug_stream_schedule): ticket list, gather order, element tasks per chunk.
+int streamSchedule(int nn, int64_t nEl, int64_t nNode, const int32_t* conn, const int32_t* order, int64_t CE, int EPT, int NPT, int D,
+                   std::vector<int2>& tasks, std::vector<int32_t>& gatherNodes, std::vector<int32_t>& target) {
     const int64_t nChunks = (nEl + CE - 1) / CE;
     if (nChunks >= (1 << 22)) return fail(EWB_ERR_UNSUPPORTED, "stream schedule: too many chunks");
-    const bool ordered = !p->elOrderHost.empty();
     // chunk of every element
     std::vector<int32_t> chunkOf((size_t)nEl);
-    for (int64_t pos = 0; pos < nEl; ++pos) chunkOf[ordered ? p->elOrderHost[pos] : pos] = (int32_t)(pos / CE);
+    for (int64_t pos = 0; pos < nEl; ++pos) chunkOf[order ? order[pos] : pos] = (int32_t)(pos / CE);
     // ready chunk of every node (nodes without elements: chunk 0)
     std::vector<int32_t> ready((size_t)nNode, 0);
     for (int64_t e = 0; e < nEl; ++e)
         for (int a = 0; a < nn; ++a) {
-            int32_t& r = ready[p->connHost[e * nn + a]];
+            int32_t& r = ready[conn[e * nn + a]];
             r = std::max(r, chunkOf[e]);
         }
     // nodes by ready chunk, ascending node inside a chunk (counting sort)
     std::vector<int64_t> gPtr((size_t)nChunks + 1, 0);
     for (int64_t n = 0; n < nNode; ++n) gPtr[ready[n] + 1]++;
     for (int64_t c = 0; c < nChunks; ++c) gPtr[c + 1] += gPtr[c];
-    std::vector<int32_t> gatherNodes((size_t)nNode);
+    gatherNodes.assign((size_t)nNode, 0);
     {
         std::vector<int64_t> cur(gPtr.begin(), gPtr.end() - 1);
         for (int64_t n = 0; n < nNode; ++n) gatherNodes[cur[ready[n]]++] = (int32_t)n;
     }
-    std::vector<int2> tasks;
+    tasks.clear();
     tasks.reserve((size_t)(nEl / EPT + nNode / NPT + 2 * nChunks + 16));
-    std::vector<int32_t> target((size_t)nChunks, 0);
+    target.assign((size_t)nChunks, 0);
     auto pushGather = [&](int64_t c) {
         for (int64_t g = gPtr[c]; g < gPtr[c + 1]; g += NPT) {
             const int cnt = (int)std::min<int64_t>(NPT, gPtr[c + 1] - g);
@@ -262,6 +258,18 @@ int streamBuild(ewb_plan* p) {
     }
     for (int64_t c = std::max<int64_t>(0, nChunks - D); c < nChunks; ++c) pushGather(c);
     if (tasks.size() >= ((size_t)1 << 30)) return fail(EWB_ERR_UNSUPPORTED, "stream schedule: too many tasks");
+    return EWB_OK;
+}
+
+int streamBuild(ewb_plan* p) {
+    streamRelease(p);
+    const bool ordered = !p->elOrderHost.empty();
+    std::vector<int2> tasks;
+    std::vector<int32_t> gatherNodes, target;
+    if (int rc = streamSchedule(p->nn, p->nEl, p->nNode, p->connHost.data(), ordered ? p->elOrderHost.data() : nullptr, p->streamChunk,
+                                p->streamElPerTask, p->streamNodesPerTask, p->streamDelay, tasks, gatherNodes, target))
+        return rc;
+    const int64_t nChunks = (int64_t)target.size();
     p->streamNTasks = (int)tasks.size();
     p->streamNChunks = (int)nChunks;
     int rc = EWB_OK;
@@ -635,6 +643,25 @@ int ewb_plan_set_element_order(ewb_plan* p, const int32_t* order_host) {
     }
     streamRelease(p);  // rebuilt at the next assembly
     return EWB_OK;
+}
+
+int64_t ewb_debug_stream_schedule(int nn, int64_t n_el, int64_t n_node, const int32_t* conn_host, const int32_t* order_host, int chunk, int delay,
+                                  int el_per_task, int nodes_per_task, int32_t* tasks_out, int64_t max_tasks, int32_t* gather_nodes_out,
+                                  int32_t* chunk_target_out, int64_t max_chunks) {
+    if (!conn_host || !tasks_out || !gather_nodes_out || !chunk_target_out || nn < 1 || n_el < 1 || n_node < 1 || chunk < 1 || delay < 0 ||
+        el_per_task < 1 || el_per_task > 127 || nodes_per_task < 1 || nodes_per_task > 32)
+        return fail(EWB_ERR_ARG, "ewb_debug_stream_schedule: bad arguments");
+    std::vector<int2> tasks;
+    std::vector<int32_t> gatherNodes, target;
+    if (int rc = streamSchedule(nn, n_el, n_node, conn_host, order_host, chunk, el_per_task, nodes_per_task, delay, tasks, gatherNodes, target)) return rc;
+    if ((int64_t)tasks.size() > max_tasks || (int64_t)target.size() > max_chunks) return fail(EWB_ERR_ARG, "ewb_debug_stream_schedule: output too small");
+    for (size_t t = 0; t < tasks.size(); ++t) {
+        tasks_out[2 * t] = tasks[t].x;
+        tasks_out[2 * t + 1] = tasks[t].y;
+    }
+    std::copy(gatherNodes.begin(), gatherNodes.end(), gather_nodes_out);
+    std::copy(target.begin(), target.end(), chunk_target_out);
+    return (int64_t)tasks.size();
 }
 
 int ewb_compute_elements_vij(ewb_plan* p, int material, const double* props, int n_props, const ewb_buffers* b, double* pe_dev, int flags,

@@ -117,6 +117,14 @@ int ewb_plan_set_gather_order(ewb_plan* plan, const int32_t* order_host);
  * centroids) keeps the element matrices in L2 between the two.  Results do not depend on it (the summation order per node is
  * always ascending element index = ascending COO index, csrgenerator.pyx:100-115).  NULL restores the element order. */
 int ewb_plan_set_element_order(ewb_plan* plan, const int32_t* order_host);
+/* Test hook, host only (no CUDA call): the ticket list of the task-stream kernel for a connectivity.  tasks_out[2 t] =
+ * key << 8 | count << 1 | kind (kind 0: element task, key = its chunk, tasks_out[2 t + 1] = first position in the processing order;
+ * kind 1: gather task, key = last chunk it waits for, tasks_out[2 t + 1] = first position in gather_nodes_out), chunk_target_out[c] =
+ * element tasks of chunk c.  Returns the number of tasks.  Invariant checked by tests/test_stream_schedule.py: a gather task's nodes
+ * only touch elements of chunks <= key, and every element task of those chunks has a lower ticket (no deadlock for any grid size). */
+int64_t ewb_debug_stream_schedule(int nn, int64_t n_el, int64_t n_node, const int32_t* conn_host, const int32_t* order_host, int chunk, int delay,
+                                  int el_per_task, int nodes_per_task, int32_t* tasks_out, int64_t max_tasks, int32_t* gather_nodes_out,
+                                  int32_t* chunk_target_out, int64_t max_chunks);
 
 /* ---- the hot path ---------------------------------------------------------------------------
  * One NIST.computeElements pass + CSRGenerator.updateCSR on the device
