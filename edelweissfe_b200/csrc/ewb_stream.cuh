@@ -1,19 +1,21 @@
 // Task-stream kernel of the arbitrary-mesh path: NIST.computeElements (nonlinearimplicitstatic.py:794-849) and
-// CSRGenerator.updateCSR (csrgenerator.pyx:100-115) as ONE persistent launch for 20-node hexahedra.
+// CSRGenerator.updateCSR (csrgenerator.pyx:100-115) as ONE persistent launch for 20-node hexahedra.  OPT-IN (EWB_STREAM=1): on B200 it
+// is slower than the two-phase path it was meant to replace — measurements and the reason in DESIGN.md §4.5.
 //
-// Why: the two-phase path (ewb_generic.cuh) writes the element matrices to a scratch, ends the kernel and reads the scratch back
+// Idea: the two-phase path (ewb_generic.cuh) writes the element matrices to a scratch, ends the kernel and reads the scratch back
 // in a second kernel: 37.9 GB of DRAM traffic per step against 11.4 GB algorithmic at 100 x 100 x 50 C3D20, and the FP64-bound
 // element kernel and the LSU-bound row gather run one after the other.  Here both are *warp tasks* of one kernel:
-//   * compute task: one warp = one element (phase A, residual row, phase B on the FP64 tensor pipe), Ke -> row scratch;
+//   * element task: one warp = one element (phase A, residual row, phase B on the FP64 tensor pipe), Ke -> row scratch;
 //   * gather task : one warp = one node, sums the rows of its incident elements in ascending element order (the reference's COO order)
 //                   into its three CSR rows, P and F;
-// handed out in a fixed order by a ticket counter.  The order (built once per plan on the host, `StreamSchedule`) interleaves the
-// gather of the nodes whose last incident element lies in element chunk c with the element tasks of chunk c + D, so a scratch row
-// is read a few microseconds after it was written — from L2, by a warp that shares its SM with element warps (tensor pipe and LSU
-// pipe overlap).  A row has exactly one reader (the scratch holds the full Ke, both triangles), which discards its L2 lines after the
-// read (`discard.global.L2`): the scratch does not have to be written back to DRAM.
+// handed out in a fixed order by a ticket counter.  The order (built once per plan on the host, streamSchedule in ewb_api.cu)
+// interleaves the gather of the nodes whose last incident element lies in element chunk c with the element tasks of chunk c + D.
+// A row has exactly one reader (the scratch holds the full Ke, both triangles), which discards its L2 lines after the read
+// (`discard.global.L2`): a row that is still in L2 when it is consumed never costs DRAM traffic.  What was measured: the discard works,
+// but the L2 keeps < 1000 elements' rows while 1776 elements are in flight (one warp each, 12 warps per SM), so most rows take the
+// round trip through DRAM anyway, and the gather inherits the element task's low occupancy.
 // Dependencies: a gather task waits (bounded) on per-chunk completion counters; it only ever depends on tasks with a lower ticket,
-// which are running on resident warps that never wait themselves — no deadlock for any grid size.
+// which are running on resident warps that never wait themselves — no deadlock for any grid size (tests/test_stream_schedule.py).
 // Results are bitwise those of the two-phase path (same blocks, same summation order), for any element processing order.
 #pragma once
 #include "ewb_generic.cuh"
