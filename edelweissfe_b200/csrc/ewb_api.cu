@@ -123,6 +123,8 @@ struct ewb_plan {
     int streamDiscard = 1;   // EWB_STREAM_DISCARD, read once at plan creation
     int streamEnabled = 0;   // EWB_STREAM=1 selects the task-stream kernel for 20-node hexahedra (read once at plan creation)
     int streamChunk = 256, streamDelay = 12, streamElPerTask = 2, streamNodesPerTask = 8;  // EWB_STREAM_CHUNK / _DELAY / _EPT / _NPT
+    int rowsVariant = 0;      // EWB_ROWS_VARIANT
+    int rowsTwoPhase = 0;     // EWB_C3D20_ROWS=1: element kernel + row gather over the row scratch as two ordinary launches
     int streamCtasPerSm = 0;  // EWB_STREAM_CTAS: cap of resident CTAs per SM (0 = occupancy limit)
     int fusedVariant = 0;  // 0 = automatic (measured best per material); 1 = first-generation sweep; else row-pipelined kernel variant (EWB_KERNEL, read once at plan creation)
 };
@@ -302,11 +304,37 @@ int streamLaunchT(ewb_plan* p, const ewb::StreamArgs& a, const ewb::MatParams& m
     return EWB_OK;
 }
 
-// ewb_assemble for 20-node hexahedra on the task-stream kernel; EWB_ERR_UNSUPPORTED = use the two-phase path
+// the two task bodies of the stream kernel as two ordinary launches over the row scratch (EWB_C3D20_ROWS=1)
+template <int NGP, int MC, int MINB>
+int rowsLaunchT(ewb_plan* p, const ewb::StreamArgs& a, const ewb::MatParams& mp, cudaStream_t st) {
+    constexpr int WARPS = 4, GW = 8, NPT = 4;
+    using L = ewb::TileLayout<20, NGP, MC>;
+    const int stride = L::PER_EL;
+    const size_t smemE = (size_t)WARPS * stride * sizeof(double);
+    auto kernE = ewb::rowElementsKernel<20, NGP, MC, WARPS, MINB>;
+    CUDA_TRY(cudaFuncSetAttribute(kernE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemE));
+    kernE<<<(unsigned)((p->nEl + WARPS - 1) / WARPS), WARPS * 32, smemE, st>>>(a, mp, stride);
+    LAUNCH_CHECK();
+    const int64_t warpsNeeded = (p->nNode + NPT - 1) / NPT;
+    auto launchG = [&](auto kernG, int gw) -> int {
+        const size_t smemG = (size_t)gw * 9 * p->maxDeg * sizeof(double);
+        CUDA_TRY(cudaFuncSetAttribute(kernG, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemG));
+        kernG<<<(unsigned)((warpsNeeded + gw - 1) / gw), gw * 32, smemG, st>>>(a, p->maxDeg, NPT);
+        LAUNCH_CHECK();
+        return EWB_OK;
+    };
+    // rows in flight per lane x occupancy (EWB_ROWS_VARIANT, tuning knob): 0: 4 rows, 24 warps per SM; 1: 8 rows, 8 warps; 2: 8 rows, 12 warps
+    if (p->rowsVariant == 1) return launchG(ewb::rowGatherKernel<20, GW, 8, 1>, GW);
+    if (p->rowsVariant == 2) return launchG(ewb::rowGatherKernel<20, 4, 8, 3>, 4);
+    return launchG(ewb::rowGatherKernel<20, GW, 4, 3>, GW);
+}
+
+// ewb_assemble for 20-node hexahedra on the row scratch: task-stream kernel (EWB_STREAM=1) or its two task bodies as two launches
+// (EWB_C3D20_ROWS=1); EWB_ERR_UNSUPPORTED = use the half-block two-phase path
 int streamAssemble(ewb_plan* p, int mc, const ewb::MatParams& mp, const ewb_buffers* b, int flags, cudaStream_t st) {
-    if (p->nn != 20 || !p->streamEnabled || p->maxDeg > 255) return EWB_ERR_UNSUPPORTED;
+    if (p->nn != 20 || !(p->streamEnabled || p->rowsTwoPhase) || p->maxDeg > 255) return EWB_ERR_UNSUPPORTED;
     if (mc != ewb::MC_LE && mc != ewb::MC_VM) return EWB_ERR_UNSUPPORTED;
-    if (!p->streamBuilt)
+    if (p->streamEnabled && !p->streamBuilt)
         if (int rc = streamBuild(p)) return rc;
     using RL = ewb::RowLayout<20>;
     if (!p->streamRows) CUDA_TRY(cudaMalloc((void**)&p->streamRows, (size_t)p->nEl * RL::SE * sizeof(double)));
@@ -327,6 +355,13 @@ int streamAssemble(ewb_plan* p, int mc, const ewb::MatParams& mp, const ewb_buff
     a.accumulate = (flags & EWB_FLAG_ACCUMULATE_PF) ? 1 : 0;
     a.discard = p->streamDiscard;
     a.wantK = (flags & EWB_FLAG_NO_STIFFNESS) ? 0 : 1;
+    if (!p->streamEnabled) {  // two ordinary launches
+        a.discard = 0;
+        a.tasks = nullptr; a.nTasks = 0; a.elOrder = nullptr; a.gatherNodes = nullptr; a.chunkTarget = nullptr; a.nChunks = 0; a.sync = nullptr;
+        if (p->ngp == 27) return mc == ewb::MC_LE ? rowsLaunchT<27, ewb::MC_LE, 3>(p, a, mp, st) : rowsLaunchT<27, ewb::MC_VM, 1>(p, a, mp, st);
+        if (p->ngp == 8) return mc == ewb::MC_LE ? rowsLaunchT<8, ewb::MC_LE, 3>(p, a, mp, st) : rowsLaunchT<8, ewb::MC_VM, 2>(p, a, mp, st);
+        return EWB_ERR_UNSUPPORTED;
+    }
     if (p->ngp == 27) {
         if (mc == ewb::MC_LE) return streamLaunchT<27, ewb::MC_LE, 3>(p, a, mp, st);
         return streamLaunchT<27, ewb::MC_VM, 1>(p, a, mp, st);
@@ -437,6 +472,8 @@ int ewb_plan_create(ewb_plan** out, int el_type, int64_t n_el, int64_t n_node, c
     p->streamElPerTask = envInt("EWB_STREAM_EPT", 2, 1, 127);
     p->streamNodesPerTask = envInt("EWB_STREAM_NPT", 8, 1, 32);
     p->streamCtasPerSm = envInt("EWB_STREAM_CTAS", 0, 0, 32);
+    p->rowsTwoPhase = envInt("EWB_C3D20_ROWS", 0, 0, 1);
+    p->rowsVariant = envInt("EWB_ROWS_VARIANT", 0, 0, 2);
     *out = p;
     return EWB_OK;
 }

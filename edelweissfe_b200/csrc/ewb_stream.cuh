@@ -232,11 +232,10 @@ __device__ __forceinline__ void streamElement(const StreamArgs& A, const MatPara
 // and shared-memory budget is the element task's), so the task keeps its own loads in flight: the node records of the whole task
 // are fetched at once, the incidence list of the next node travels while the current node is summed, and the rows of up to
 // eight incident elements (24 x 128-bit loads per lane) are requested before the first one is added.
-template <int NN>
+template <int NN, int B = 8>  // B: incident elements per batch (rows in flight per lane: 3 B 128-bit loads)
 __device__ __forceinline__ void streamGatherTask(const StreamArgs& A, double* buf, int first, int cnt, int lane) {
     using RL = RowLayout<NN>;
     static_assert(RL::RS == 64, "lane = two columns of a row");
-    constexpr int B = 8;  // incident elements per batch
     const int p0 = 2 * lane, p1 = 2 * lane + 1;
     const int b0 = p0 / 3, j0 = p0 - 3 * b0, b1 = p1 / 3, j1 = p1 - 3 * b1;
     const bool isK = lane < (3 * NN) / 2 && A.wantK, isP = lane == (3 * NN) / 2;  // lane 30: column 60 = residual
@@ -244,7 +243,7 @@ __device__ __forceinline__ void streamGatherTask(const StreamArgs& A, double* bu
     // (32-bit: 9 * slots = nnz and the incidence count both fit an int, checked at plan creation)
     int nodeL = 0, s0L = 0, s1L = 0, k0L = 0, k1L = 0;
     if (lane < cnt) {
-        nodeL = A.gatherNodes[first + lane];
+        nodeL = A.gatherNodes ? A.gatherNodes[first + lane] : first + lane;
         s0L = (int)A.adjPtr[nodeL];
         s1L = (int)A.adjPtr[nodeL + 1];
         k0L = (int)A.incPtr[nodeL];
@@ -279,7 +278,9 @@ __device__ __forceinline__ void streamGatherTask(const StreamArgs& A, double* bu
                 eaNext = (lane < B && n0 + lane < n1) ? A.inc[n0 + lane] : -1;
             }
             double2 v[B][3];
-            int dd[B];  // destination columns of the lane's two values, 16 bits each
+            // slots of the lane's two values in the node's sorted neighbour list: RAW bytes here, arithmetic only after all loads of
+            // the batch are issued (a use inside the issue loop makes every element's loads wait for the previous element's slots)
+            unsigned char sb0[B], sb1[B];
             auto rowOf = [&](int u) -> const double* {
                 const int32_t ea = __shfl_sync(0xffffffffu, eaL, u);
                 if (ea < 0) return nullptr;
@@ -296,7 +297,10 @@ __device__ __forceinline__ void streamGatherTask(const StreamArgs& A, double* bu
 #pragma unroll
                         for (int i = 0; i < 3; ++i) v[u][i] = __ldcg(src + i * (RL::RS / 2));
                     }
-                    if (isK) dd[u] = (3 * A.slotTab[(int64_t)(kb + u) * NN + b0] + j0) | ((3 * A.slotTab[(int64_t)(kb + u) * NN + b1] + j1) << 16);
+                    if (isK) {
+                        sb0[u] = A.slotTab[(int64_t)(kb + u) * NN + b0];
+                        sb1[u] = A.slotTab[(int64_t)(kb + u) * NN + b1];
+                    }
                 }
             }
 #pragma unroll
@@ -304,7 +308,7 @@ __device__ __forceinline__ void streamGatherTask(const StreamArgs& A, double* bu
                 const double* rp = rowOf(u);
                 if (rp != nullptr) {  // warp-uniform
                     if (isK) {
-                        const int d0 = dd[u] & 0xffff, d1 = dd[u] >> 16;
+                        const int d0 = 3 * sb0[u] + j0, d1 = 3 * sb1[u] + j1;
 #pragma unroll
                         for (int i = 0; i < 3; ++i) {
                             buf[i * rowLen + d0] += v[u][i].x;
@@ -369,6 +373,29 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) streamKernel(const __grid_co
         }
         t = __shfl_sync(0xffffffffu, tn, 0);
     }
+}
+
+// ---- the same two task bodies as two ordinary kernels ("row" two-phase path, EWB_C3D20_ROWS=1): every warp of the first launch
+// computes one element into the row scratch, every warp of the second gathers `npt` consecutive nodes.  Against the half-block
+// two-phase path of ewb_generic.cuh: the scratch is read once instead of twice and with whole-line loads (the gather is no longer
+// LSU bound), at the price of writing both triangles (15.4 instead of 8.8 GB at 100 x 100 x 50).  Same results, bitwise.
+template <int NN, int NGP, int MC, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) rowElementsKernel(const __grid_constant__ StreamArgs A, const MatParams mp, int warpStride) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t e = (int64_t)blockIdx.x * WARPS + warp;
+    if (e >= A.nEl) return;
+    streamElement<NN, NGP, MC>(A, mp, smem + (size_t)warp * warpStride, e, lane);
+}
+
+template <int NN, int WARPS, int B, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) rowGatherKernel(const __grid_constant__ StreamArgs A, int maxDeg, int npt) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t first = ((int64_t)blockIdx.x * WARPS + warp) * npt;
+    if (first >= A.nNode) return;
+    const int cnt = (int)min((int64_t)npt, A.nNode - first);
+    streamGatherTask<NN, B>(A, smem + (size_t)warp * 9 * maxDeg, (int)first, cnt, lane);
 }
 
 }  // namespace ewb

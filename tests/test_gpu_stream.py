@@ -19,7 +19,7 @@ def _run(elType, material, props, n, scale, env, monkeypatch, order="morton", fl
 
     from edelweissfe_b200 import ElementAssembly, box_mesh
 
-    for k in ("EWB_STREAM", "EWB_STREAM_DISCARD", "EWB_STREAM_CHUNK", "EWB_STREAM_DELAY", "EWB_STREAM_EPT", "EWB_STREAM_NPT"):
+    for k in ("EWB_STREAM", "EWB_STREAM_DISCARD", "EWB_STREAM_CHUNK", "EWB_STREAM_DELAY", "EWB_STREAM_EPT", "EWB_STREAM_NPT", "EWB_C3D20_ROWS"):
         monkeypatch.delenv(k, raising=False)
     monkeypatch.setenv("EWB_STREAM", "1")  # the task-stream kernel is opt-in
     for k, v in env.items():
@@ -77,6 +77,7 @@ CASES = [
         ({"EWB_STREAM_CHUNK": 1, "EWB_STREAM_DELAY": 0, "EWB_STREAM_EPT": 1, "EWB_STREAM_NPT": 1}, "random"),
         ({"EWB_STREAM_CHUNK": 7, "EWB_STREAM_DELAY": 1, "EWB_STREAM_EPT": 3, "EWB_STREAM_NPT": 5, "EWB_STREAM_DISCARD": 0}, "random"),
         ({"EWB_STREAM_CHUNK": 4096, "EWB_STREAM_DELAY": 3}, "morton"),
+        ({"EWB_STREAM": 0, "EWB_C3D20_ROWS": 1}, "none"),  # the two task bodies as two ordinary launches over the row scratch
     ],
 )
 def test_stream_equals_two_phase_bitwise(elType, material, props, n, scale, env, order, monkeypatch):
