@@ -68,6 +68,8 @@ SYMBOLS = {
     "ewb_assemble": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(EwbBuffers), C.POINTER(C.c_double), C.c_double, C.c_int, _P]),
     "ewb_plan_x_chunks": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, _P, C.c_int]),
     "ewb_assemble_chunks": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(EwbBuffers), C.c_int, C.c_int, C.c_int, _P]),
+    "ewb_host_register": (C.c_int, [_P, C.c_int64]),
+    "ewb_host_unregister": (C.c_int, [_P]),
     "ewb_poll_status": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
     "ewb_compute_elements_vij": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(EwbBuffers), _P, C.c_int, _P]),
     "ewb_update_csr": (C.c_int, [_P, _P, _P, _P]),

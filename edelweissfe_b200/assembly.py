@@ -360,22 +360,22 @@ class ElementAssembly:
                 owner = owner.base
             if owner.ctypes.data != arr.ctypes.data or owner.nbytes != arr.nbytes:
                 return None
-            rt = torch.cuda.cudart()
-            if int(rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)) != 0:
-                return None
+            lib = self.lib
             ptr = arr.ctypes.data
+            if lib.ewb_host_register(C.c_void_p(ptr), arr.nbytes) != 0:
+                return None
 
-            def _release(ptr=ptr, key=key, reg=reg):
+            def _release(ptr=ptr, key=key, reg=reg, lib=lib):
                 reg.pop(key, None)
                 try:
-                    torch.cuda.cudart().cudaHostUnregister(ptr)
+                    lib.ewb_host_unregister(C.c_void_p(ptr))
                 except Exception:  # noqa: BLE001 - interpreter shutdown
                     pass
 
             try:
                 weakref.finalize(owner, _release)
             except TypeError:
-                rt.cudaHostUnregister(ptr)
+                lib.ewb_host_unregister(C.c_void_p(ptr))
                 return None
             reg[key] = True
         t = torch.from_numpy(arr.reshape(-1))

@@ -859,6 +859,27 @@ int ewb_assemble_chunks(ewb_plan* p, int material, const double* props, int n_pr
     return EWB_OK;
 }
 
+// Pin a caller-owned host array in place (the solver's dU lives for a whole step): its upload then needs no staging copy.
+int ewb_host_register(void* ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return fail(EWB_ERR_ARG, "ewb_host_register: bad arguments");
+    const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // not sticky, but it must not show up in the next launch check
+        return fail(EWB_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+    }
+    return EWB_OK;
+}
+
+int ewb_host_unregister(void* ptr) {
+    if (!ptr) return fail(EWB_ERR_ARG, "ewb_host_unregister: null pointer");
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(EWB_ERR_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e));
+    }
+    return EWB_OK;
+}
+
 int ewb_body_force(ewb_plan* p, const double* coords_dev, const double load_host[3], double* pext_dev, void* stream) {
     if (!p || !coords_dev || !load_host || !pext_dev) return fail(EWB_ERR_ARG, "ewb_body_force: bad arguments");
     WITH_DEVICE(p->device);

@@ -141,6 +141,11 @@ int ewb_assemble(ewb_plan* plan, int material, const double* props_host, int n_p
 int ewb_plan_x_chunks(ewb_plan* plan, int material, const double* props_host, int n_props, int flags, int32_t* bounds_out, int max_bounds);
 int ewb_assemble_chunks(ewb_plan* plan, int material, const double* props_host, int n_props, const ewb_buffers* buf, int flags,
                         int chunk_begin, int chunk_end, void* stream);
+/* Pin / unpin a caller-owned host array in place (cudaHostRegister): the solver's dU vector lives for a whole step
+ * (nonlinearimplicitstatic.py:163), so the host layer registers it once and uploads from it directly instead of staging it
+ * through a pinned copy.  A failure (e.g. locked-memory limit) leaves no CUDA error state behind; the caller falls back to staging. */
+int ewb_host_register(void* host_ptr, int64_t bytes);
+int ewb_host_unregister(void* host_ptr);
 /* Synchronises `stream`, returns EWB_OK or EWB_CUTBACK (then *pNewDT = 0.5). */
 int ewb_poll_status(ewb_plan* plan, void* stream, double* pNewDT);
 
