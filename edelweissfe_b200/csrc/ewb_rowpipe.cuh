@@ -654,7 +654,9 @@ int launchRowPipe(SweepPlan& sp, const MatParams& mp, const ewb_buffers* b, int*
     if (rowsMax < 1) return EWB_ERR_UNSUPPORTED;
     SweepArgs a;
     sp.fillCommon(a, mp, b, failFlag, flags);
-    const RowPipeTiling t = rowPipeTiling<TZ>(sp.nX, sp.nY, sp.nZ, sp.nSM, rowsMax, sp.chunkOverride);
+    const bool piecewise = sp.tilingOut != nullptr || sp.chunkEnd >= 0;  // ewb_plan_x_chunks / ewb_assemble_chunks
+    const int pipeChunks = sp.pipeChunks >= 0 ? sp.pipeChunks : (sp.chunkOverride == 0 && sp.nX + 1 >= 48 ? 6 : 0);
+    const RowPipeTiling t = rowPipeTiling<TZ>(sp.nX, sp.nY, sp.nZ, sp.nSM, rowsMax, piecewise && pipeChunks > 0 ? pipeChunks : sp.chunkOverride);
     a.tilesY = t.tilesY; a.tilesZ = t.tilesZ; a.tileRows = t.tileRows; a.chunkLen = t.chunkLen; a.nChunks = t.nChunks;
     if (sp.tilingOut != nullptr) {  // query only (ewb_plan_x_chunks)
         sp.tilingOut[0] = t.chunkLen;

@@ -559,3 +559,29 @@ def test_chunk_pipelined_increment_is_bitwise(material, props, monkeypatch):
     a2.begin_increment(U_n)
     P2, f2 = a2.compute_host_increment_pipelined(dU)
     assert np.abs(P2 - P0).max() <= 1e-12 * np.abs(P0).max()
+
+
+@pytest.mark.parametrize("material,props", [("linearelastic", [2.1e4, 0.22]), ("vonmises", [2.1e4, 0.22, 355, 1000, 200, 1400])])
+def test_pipeline_chunking_does_not_change_results(material, props, monkeypatch):
+    """The chunk-by-chunk launches may use a finer x-chunking than the single launch (EWB_PIPE_CHUNKS; automatic: six chunks for boxes
+    of >= 48 node planes): chunks are independent and every CSR row is summed in the same order whatever the chunking — bit for bit."""
+    from edelweissfe_b200 import ElementAssembly, box_mesh
+
+    monkeypatch.setenv("EWB_PIPE_CHUNKS", "3")
+    monkeypatch.delenv("EWB_CHUNKS", raising=False)
+    n = (25, 9, 17)
+    coords, conn = box_mesh(*n)
+    rng = np.random.default_rng(8)
+    a0 = ElementAssembly("C3D8", conn, coords, material, props, box=n)
+    a1 = ElementAssembly("C3D8", conn, coords, material, props, box=n)
+    assert len(a1.x_chunks()) - 1 == 3
+    U_n = 1e-3 * rng.standard_normal(a0.nDof)
+    dU = 3e-3 * rng.standard_normal(a0.nDof)
+    a0.begin_increment(U_n)
+    a1.begin_increment(U_n)
+    P0, f0 = a0.compute_host_increment(dU)  # one launch, the single-launch tiling
+    P0 = P0.copy()
+    P1, f1 = a1.compute_host_increment_pipelined(dU)  # three launches
+    assert np.array_equal(P0, P1) and f0 == f1
+    for name in ("csr_data", "F", "state_temp"):
+        assert np.array_equal(getattr(a0, name).cpu().numpy(), getattr(a1, name).cpu().numpy()), name
