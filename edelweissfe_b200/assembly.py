@@ -53,6 +53,20 @@ def morton_order(coords: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(np.argsort(key, kind="stable").astype(np.int32))
 
 
+def pipeline_pieces(bounds, plane_dofs):
+    """Dof ranges of the chunk pipeline (pure index logic; tests/test_pipeline_pieces.py).  bounds: node-plane boundaries of the
+    fused kernel's x-chunks (ewb_plan_x_chunks).  Chunk c reads U / dU of the node planes [bounds[c] - 1, bounds[c + 1]] and writes
+    P / F of [bounds[c], bounds[c + 1]).  Returns per chunk (up_lo, up_hi, down_lo, down_hi): the part of dU that has to be uploaded
+    before chunk c can run and was not uploaded for an earlier chunk, and the part of P that is final once chunk c has run."""
+    n_planes = bounds[-1]
+    out = []
+    for c in range(len(bounds) - 1):
+        lo = 0 if c == 0 else (bounds[c] + 1) * plane_dofs
+        hi = min(bounds[c + 1] + 1, n_planes) * plane_dofs
+        out.append((lo, max(lo, hi), bounds[c] * plane_dofs, bounds[c + 1] * plane_dofs))
+    return out
+
+
 class ElementAssembly:
     def __init__(self, elType, conn, coords, material, props, device="cuda:0", box=None):
         self.lib = _lib.load()
@@ -419,9 +433,7 @@ class ElementAssembly:
         pd = self.nDof // nPlanes  # dofs per node plane
         buf = self._buffers()
         done = []
-        for c in range(len(bounds) - 1):
-            lo = 0 if c == 0 else (bounds[c] + 1) * pd  # chunk c reads planes [bounds[c] - 1, bounds[c + 1]]: the new ones
-            hi = min(bounds[c + 1] + 1, nPlanes) * pd
+        for c, (lo, hi, a, b) in enumerate(pipeline_pieces(bounds, pd)):
             if dU is not None and hi > lo:
                 hdU_np[lo:hi] = dU[lo:hi]  # pageable input: staged chunk by chunk, behind the previous chunk's upload and kernel
             with torch.cuda.stream(st["h2d"]):
@@ -440,10 +452,9 @@ class ElementAssembly:
             kd = torch.cuda.Event()
             kd.record(ks)
             done.append(kd)
-            if launch is None:  # (a slab's first plane still receives the lower neighbour's rows: its P is downloaded at the end)
+            if launch is None:
                 st["d2h"].wait_event(kd)
                 with torch.cuda.stream(st["d2h"]):
-                    a, b = bounds[c] * pd, bounds[c + 1] * pd
                     hP[a:b].copy_(self.P[a:b], non_blocking=True)
         for kd in done:
             cur.wait_event(kd)
